@@ -1,0 +1,217 @@
+"""Generate the golden fixtures in this directory FROM THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+For every reduced-width spec in porous_cfd_b200.synthetic it
+  1. builds the reference's own model class (models/pipn/*, models/pi_gano/*) through
+     oracle/ref_shim.py, default-initialised with torch.manual_seed(3) and weight matrices x3,
+  2. runs `model.training_step(batch, 0)` exactly as written + `loss.backward()` (parity of
+     record, laplacian='reference') and, separately, the same step with the documented call
+     `get_laplacian(points, get_jacobian(points, U))` (laplacian='true') using the reference's
+     own helper functions and loss modules,
+  3. asserts that the stand-alone oracle (oracle/pinn_oracle.py) reproduces both,
+  4. writes inputs, parameters and the REFERENCE's outputs to <spec>.npz.
+
+It also writes index fixtures for fps / radius (third-party restatement; parity unpinned) and the
+manufactured-solution known-answer check (examples/manufactured_solutions/manufactured_dataset.py:46-67).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import pcfd_import  # noqa: E402
+
+pcfd_import.load()
+from oracle import pinn_oracle, pyg_restate, ref_shim  # noqa: E402
+from porous_cfd_b200 import synthetic  # noqa: E402
+
+TINY = ['tiny_pipn', 'tiny_pipn_pp', 'tiny_pigano', 'tiny_pigano_pp', 'tiny_manufactured_pp', 'tiny_manufactured']
+SHAPE = dict(n_geometries=2, n_internal=40, n_boundary=24, n_obs=10)
+
+
+def build_reference_model(spec: dict):
+    """Instantiate the reference class named by spec['kind'] with the reference's own scaler objects."""
+    from dataset.foam_dataset import Normalizer, StandardScaler
+    from models.losses import FixedLossScaler
+    from models.pi_gano.pi_gano import PiGano
+    from models.pi_gano.pi_gano_pp import PiGanoPp
+    from models.pipn.pipn_baseline import PipnManufactured, PipnManufacturedPorousPp
+    from models.pipn.pipn_foam import PipnFoam, PipnFoamPp
+    from torch.nn import SiLU, Tanh
+
+    act = {'silu': SiLU, 'tanh': Tanh}[spec['activation']]
+    dims = spec['dims']
+    scalers = loss_scaler = None
+    if spec['loss'] != 'manufactured':
+        sc = spec['scalers']
+        scalers = {'C': StandardScaler(sc['C_std'].numpy().astype(np.float64), sc['C_mean'].numpy().astype(np.float64)),
+                   'U': StandardScaler(sc['U_std'].numpy().astype(np.float64), sc['U_mean'].numpy().astype(np.float64)),
+                   'p': StandardScaler(sc['p_std'].numpy().astype(np.float64), sc['p_mean'].numpy().astype(np.float64)),
+                   'd': Normalizer(sc['d_min'].numpy().astype(np.float64), sc['d_max'].numpy().astype(np.float64)),
+                   'f': Normalizer(sc['f_min'].numpy().astype(np.float64), sc['f_max'].numpy().astype(np.float64))}
+        w = spec['loss_weights']
+        loss_scaler = FixedLossScaler({'continuity': w[:1], 'momentum': w[1:1 + dims],
+                                       'boundary': w[1 + dims:2 + 2 * dims], 'observations': w[2 + 2 * dims:]})
+    k = spec['kind']
+    if k == 'PipnFoam':
+        m = PipnFoam(spec['nu'], spec['d'], spec['f'], spec['fe_local_layers'], spec['fe_global_layers'],
+                     spec['seg_layers'], scalers, loss_scaler, spec['seg_dropout'], act)
+    elif k == 'PipnFoamPp':
+        m = PipnFoamPp(spec['nu'], spec['d'], spec['f'], spec['fe_local_layers'], spec['fe_global_layers'],
+                       spec['fe_radius'], spec['fe_fraction'], spec['seg_layers'], scalers, loss_scaler,
+                       spec['seg_dropout'], act, spec['max_neighbors'])
+    elif k == 'PipnManufactured':
+        m = PipnManufactured(spec['nu'], spec['d'], spec['f'], spec['fe_local_layers'], spec['fe_global_layers'],
+                             spec['seg_layers'], act)
+    elif k == 'PipnManufacturedPorousPp':
+        assert spec['max_neighbors'] == 64  # the reference ctor has no max_neighbors argument
+        m = PipnManufacturedPorousPp(spec['nu'], spec['d'], spec['f'], spec['fe_local_layers'],
+                                     spec['fe_global_layers'], spec['fe_radius'], spec['fe_fraction'],
+                                     spec['seg_layers'], act)
+    elif k == 'PiGano':
+        m = PiGano(spec['nu'], spec['out_features'], spec['branch_layers'], spec['geometry_layers'],
+                   spec['local_layers'], spec['n_operators'], spec['operator_dropout'], scalers,
+                   spec['variable_boundaries'], loss_scaler, act)
+    elif k == 'PiGanoPp':
+        m = PiGanoPp(spec['nu'], spec['out_features'], spec['branch_layers'], spec['geometry_layers'],
+                     spec['geometry_radius'], spec['geometry_fraction'], spec['local_layers'], spec['n_operators'],
+                     spec['operator_dropout'], scalers, spec['variable_boundaries'], loss_scaler, act,
+                     spec['max_neighbors'])
+    else:
+        raise KeyError(k)
+    return m.to('cpu')
+
+
+def reference_step(model, spec, data, labels, domain, laplacian: str):
+    """Run the reference.  'reference' = training_step as written; 'true' = same body with the
+    documented get_laplacian(points, jacobian) call, assembled from the reference's own functions."""
+    from dataset.foam_data import FoamData
+    from models import model_base as mb
+    from models.losses import vector_loss
+    from torch.nn.functional import mse_loss
+
+    model.zero_grad()
+    batch = FoamData(data.clone(), labels, {k: v.clone() for k, v in domain.items()})
+    if laplacian == 'reference':
+        model.logged.clear()
+        loss = model.training_step(batch, 0)
+        logged = list(model.logged.values())
+        n_terms = 2 * spec['dims'] + 2 + ((spec['dims'] + 1) if spec['enable_data_loss'] else 0)
+        losses = torch.stack(logged[1:1 + n_terms])
+        p_err, u_err = logged[1 + n_terms], torch.stack(logged[2 + n_terms:])
+    else:
+        pts, all_pts = mb.enable_internal_autograd(batch)
+        pred = model.forward(all_pts, batch)
+        bnd_p = mse_loss(pred['boundary']['p'], batch['boundary']['p'])
+        bnd_u = vector_loss(pred['boundary']['U'], batch['boundary']['U'], mse_loss)
+        jac = mb.get_jacobian(pts, pred['internal']['U'])
+        lap = mb.get_laplacian(pts, jac)
+        dp = mb.calculate_gradients(pred['internal']['p'], pts)
+        cont = model.continuity_loss(jac)
+        mom = model.momentum_loss(batch['internal'], pred['internal']['U'], jac, lap, dp)
+        obs = []
+        if model.enable_data_loss:
+            obs = [*vector_loss(pred['obs']['U'], batch['obs']['U'], mse_loss),
+                   mse_loss(pred['obs']['p'], batch['obs']['p'])]
+        losses = torch.stack([cont, *mom, *bnd_u, bnd_p, *obs])
+        if model.loss_scaler is not None:
+            losses = model.loss_scaler(model, losses)
+        loss = losses.sum()
+        u_err, p_err = model.calculate_errors(batch, pred)
+    loss.backward()
+    grads = {k: (v.grad.detach().clone() if v.grad is not None else torch.zeros_like(v))
+             for k, v in model.named_parameters()}
+    return loss.detach(), losses.detach(), u_err.detach(), p_err.detach(), grads
+
+
+def rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def main():
+    ref_shim.install()
+    torch.set_num_threads(4)
+    for name in TINY:
+        spec = synthetic.model_spec(name)
+        torch.manual_seed(3)
+        model = build_reference_model(spec)
+        model.eval()  # dropout off: parity of record
+        with torch.no_grad():
+            for prm in model.parameters():
+                if prm.dim() == 2:
+                    prm.mul_(3.0)
+        params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        data, labels, domain = synthetic.make_batch(spec['layout'], seed=8421, **SHAPE)
+        out = {'data': data.numpy(), **{f'domain/{k}': v.numpy() for k, v in domain.items()},
+               **{f'param/{k}': v.numpy() for k, v in params.items()}}
+        for mode in ('reference', 'true'):
+            loss, losses, u_err, p_err, grads = reference_step(model, spec, data, labels, domain, mode)
+            orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, laplacian=mode)
+            e_loss = float(((orc['losses'].detach() - losses).abs() / (losses.abs() + 1e-30)).max())
+            gref = torch.cat([grads[k].flatten() for k in params])
+            gorc = torch.cat([orc['grads'][k].flatten() for k in params])
+            e_grad = rel(gorc, gref)
+            print(f'{name:24s} {mode:9s} loss={float(loss):.6e} terms[{len(losses)}] '
+                  f'oracle-vs-reference: loss-term max rel {e_loss:.2e}, grad rel L2 {e_grad:.2e}, '
+                  f'|grad|={float(gref.norm()):.3e}')
+            assert e_loss < 2e-5 and e_grad < 2e-5, 'stand-alone oracle disagrees with the reference'
+            assert rel(orc['u_error'], u_err) < 1e-5 and rel(orc['p_error'], p_err) < 1e-5
+            out[f'{mode}/loss'] = loss.numpy()
+            out[f'{mode}/losses'] = losses.numpy()
+            out[f'{mode}/u_error'] = u_err.numpy()
+            out[f'{mode}/p_error'] = p_err.numpy()
+            for k, g in grads.items():
+                out[f'{mode}/grad/{k}'] = g.numpy()
+        np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **out)
+
+    # ---- index fixtures (restated third-party ops: parity unpinned, fixtures freeze OUR semantics) ----
+    g = torch.Generator().manual_seed(11)
+    idx_out = {}
+    for tag, (nb, n, d, ratio, r, k) in {'a': (3, 64, 3, 0.5, 0.5, 8), 'b': (2, 200, 2, 0.25, 0.3, 16),
+                                         'c': (1, 1000, 3, 0.5, 0.5, 16)}.items():
+        pos = torch.rand(nb * n, d, generator=g) * 2 - 1
+        batch = torch.arange(nb).repeat_interleave(n)
+        idx = pyg_restate.fps(pos, batch, ratio)
+        row, col = pyg_restate.radius(pos, pos[idx], r, batch, batch[idx], k)
+        idx_out.update({f'{tag}/pos': pos.numpy(), f'{tag}/meta': np.array([nb, n, d, ratio, r, k], dtype=np.float64),
+                        f'{tag}/fps': idx.numpy(), f'{tag}/row': row.numpy(), f'{tag}/col': col.numpy()})
+    # degenerate: duplicated points (ties) -> first index wins
+    pos = torch.tensor([[0., 0.], [1., 0.], [1., 0.], [0., 1.], [0., 1.], [0.5, 0.5]])
+    idx_out['ties/pos'] = pos.numpy()
+    idx_out['ties/fps'] = pyg_restate.fps(pos, None, 0.5).numpy()
+    np.savez_compressed(os.path.join(HERE, 'index_ops.npz'), **idx_out)
+
+    # ---- manufactured-solution KAT: exact fields fed to the reference's loss modules give residual 0 ----
+    from dataset.foam_data import FoamData
+    from models.losses import ContinuityLoss, MomentumLossManufactured
+    data, labels, domain = synthetic.make_batch('manufactured', 2, 50, 10, 0, seed=5)
+    d64 = data.double()
+    internal = FoamData(d64, labels, domain)['internal']
+    x, y = internal['C'][..., 0], internal['C'][..., 1]
+    u = torch.stack([torch.sin(y) * torch.cos(x), -torch.sin(x) * torch.cos(y)], -1)
+    jac = torch.stack([torch.stack([-torch.sin(y) * torch.sin(x), torch.cos(y) * torch.cos(x)], -1),
+                       torch.stack([-torch.cos(x) * torch.cos(y), torch.sin(x) * torch.sin(y)], -1)], -2)
+    lap = torch.stack([torch.stack([-u[..., 0], -u[..., 0]], -1), torch.stack([-u[..., 1], -u[..., 1]], -1)], -2)
+    dp = torch.stack([0.5 * torch.sin(2 * x), 0.5 * torch.sin(2 * y)], -1)
+    res = MomentumLossManufactured(0.01, 50, 1).func(internal, u, jac, lap, dp)
+    div = ContinuityLoss().func(jac)
+    print('manufactured KAT: max |momentum residual| =', float(res.abs().max()), ' max |div| =', float(div.abs().max()))
+    assert float(res.abs().max()) < 1e-6 and float(div.abs().max()) < 1e-12
+    np.savez_compressed(os.path.join(HERE, 'manufactured_kat.npz'), data=data.numpy(),
+                        u=u.numpy(), jac=jac.numpy(), lap=lap.numpy(), dp=dp.numpy(),
+                        **{f'domain/{k}': v.numpy() for k, v in domain.items()})
+    print('golden fixtures written to', HERE)
+
+
+if __name__ == '__main__':
+    main()
