@@ -1,0 +1,235 @@
+/*
+ * pcfd.h -- C ABI of libpcfd_sm100.so: the B200 (sm_100a) kernels behind the physics-informed
+ * training step of Gallinator/porous-cfd.
+ *
+ * The reference is pure Python and has no FFI of its own; the seams this
+ * library is bound behind are the reference's Python call sites, cited per function below
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a PCFD_ERR_* code; nothing throws, nothing exits;
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *     the library never allocates, frees or retains memory; scratch space is passed in as
+ *     `workspace` / `workspace_bytes` (sizes from the *_workspace_bytes queries);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal syncs, so
+ *     every entry point is CUDA-graph capturable;
+ *   - fp32 data, row-major, explicit leading dimensions (`ld*`, in elements);
+ *   - "jet" tensors are stacks of `cj` channel planes [cj][rows][width]: plane 0 is the value,
+ *     planes 1..D the first spatial tangents d/dx_k, planes D+1..2D the second tangents
+ *     d2/dx_k2 (cj = 1, 1+D or 1+2D; D = 2 or 3).  `plane_stride` is the distance between
+ *     planes in elements.
+ *   - there is no CPU fallback: a device that is not sm_100 yields PCFD_ERR_ARCH.
+ */
+#ifndef PCFD_H_
+#define PCFD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCFD_ABI_VERSION 1
+
+enum {
+  PCFD_OK = 0,
+  PCFD_ERR_ARG = 1,       /* bad shape / null pointer / unsupported channel count */
+  PCFD_ERR_ALIGN = 2,     /* misaligned pointer or leading dimension */
+  PCFD_ERR_WORKSPACE = 3, /* workspace too small */
+  PCFD_ERR_ARCH = 4,      /* current device is not sm_100 */
+  PCFD_ERR_CUDA = 100     /* PCFD_ERR_CUDA + cudaError_t of a failed launch */
+};
+
+enum { PCFD_ACT_NONE = 0, PCFD_ACT_SILU = 1, PCFD_ACT_TANH = 2 };
+
+/* ABI version, and the compute capability (major*10+minor) of the current device. */
+int pcfd_abi_version(void);
+int pcfd_device_arch(int* cc_out_host);
+/* Which engine executes the jet GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32. */
+int pcfd_set_gemm_engine(int engine);
+int pcfd_get_gemm_engine(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Input transform of a jet layer.  The reference applies activation / dropout / branch scaling
+ * at the END of a layer (models/modules.py:48-52 MLP; :239-245 NeuralOperator); here the layer
+ * stores its pre-activations and the NEXT layer applies  a = dropout(act(z)) * escale  while it
+ * loads its input, carrying the jet through it:
+ *     a0 = s*f(z0)   ak = s*f'(z0)*zk   akk = s*(f''(z0)*zk^2 + f'(z0)*zkk),  s = mask/(1-p) * escale
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pcfd_intrans {
+  int32_t act;              /* PCFD_ACT_* */
+  int32_t act_cols;         /* apply act/dropout/escale to the first act_cols input columns only; <=0: all */
+  const float* escale;      /* [n_geom][k] per-geometry embedding (PI-GANO branch output) or NULL */
+  int32_t ldescale;
+  float drop_p;             /* dropout probability, 0 = off (models/modules.py:51-52, 236-237) */
+  const uint64_t* seed_dev; /* device pointer to the step seed (graph-replayable); may be NULL if drop_p == 0 */
+  uint32_t salt;            /* distinguishes layers that share the seed */
+  uint32_t reserved;
+} pcfd_intrans_t;
+
+/*
+ * Jet linear layer, forward.  Replaces torch.nn.Linear on the differentiated path
+ * (models/modules.py:48, :232; models/pi_gano/pi_gano.py:47) for value AND tangent channels:
+ *     zout[c] = T(zin)[c] * W^T   (+ bias + cvec[geom] on channel 0)
+ * w is [n][k] (torch Linear layout) with row stride ldw, so a column block of a larger weight
+ * (the per-point half of a concat layer, models/pipn/pipn_foam.py:96-98) is addressed in place.
+ * cvec [n_geom][n] carries the per-geometry constant half of such a layer; geometry of row r is
+ * r / rows_per_geom.
+ */
+int pcfd_jet_linear_fwd(const float* zin, int64_t zin_plane_stride, int32_t ldzin,
+                        const pcfd_intrans_t* tin_host,
+                        const float* w, int32_t ldw, const float* bias,
+                        const float* cvec, int32_t ldcvec,
+                        float* zout, int64_t zout_plane_stride, int32_t ldzout,
+                        int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
+                        void* stream);
+
+/*
+ * Jet linear layer, backward to the layer input: reverse of the forward above including the
+ * reverse of the input transform (needs f''' for second-order jets).  gzout is the gradient wrt
+ * zout; gzin receives the gradient wrt zin (overwritten).  gescale (optional, [n_geom][k]) is
+ * ACCUMULATED with the gradient wrt escale.  Replaces the autograd double-backward through
+ * Linear/activation (models/model_base.py:11-20 create_graph=True sweeps + loss.backward()).
+ */
+int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_plane_stride, int32_t ldgzout,
+                           const float* w, int32_t ldw,
+                           const float* zin, int64_t zin_plane_stride, int32_t ldzin,
+                           const pcfd_intrans_t* tin_host,
+                           float* gzin, int64_t gzin_plane_stride, int32_t ldgzin,
+                           float* gescale, int32_t ldgescale,
+                           int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
+                           void* stream);
+
+/*
+ * Jet linear layer, backward to the parameters.  All outputs are ACCUMULATED (+=):
+ *     gw[n][k]   += sum_{c,rows} gzout[c][row][n] * T(zin)[c][row][k]
+ *     gbias[n]   += sum_rows gzout[0][row][n]                       (optional)
+ *     gcvec[g][n]+= sum_{rows of geometry g} gzout[0][row][n]        (optional)
+ * The row reduction is split over CTAs and reduced in a fixed order (deterministic).
+ */
+size_t pcfd_jet_linear_bwd_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n);
+int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_plane_stride, int32_t ldgzout,
+                           const float* zin, int64_t zin_plane_stride, int32_t ldzin,
+                           const pcfd_intrans_t* tin_host,
+                           float* gw, int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec,
+                           int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Segmented max with arg-max: out[s][c] = max_{valid slots j} act(z[s*seg_len + j][c]).
+ * Replaces torch.max(dim=1) (models/modules.py:81, :190, :214), PyG global_max_pool (:420) and
+ * the max aggregation of PointNetConv (:277-292).  `slots` ([n_seg][seg_len] int32, <0 = empty)
+ * masks padded edge slots, NULL = all valid.  Ties -> lowest slot.  Empty segment -> 0, arg -1.
+ */
+int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots,
+                    int64_t n_seg, int32_t seg_len, int32_t c,
+                    float* out, int32_t ldout, int32_t* arg, void* stream);
+/* gz[s*seg_len + j][c] = (j == arg[s][c]) ? gout[s][c] * act'(z) : 0   (gz fully overwritten) */
+int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t* arg,
+                    const float* z, int32_t ldz, int32_t act,
+                    int64_t n_seg, int32_t seg_len, int32_t c,
+                    float* gz, int32_t ldgz, void* stream);
+
+/*
+ * Farthest point sampling, one CTA per geometry; torch_cluster.fps(pos, batch, ratio) as called at
+ * models/modules.py:320 with a deterministic start (first point; upstream default is random).
+ * pos [n_geom][n][dims]; m = ceil(ratio*n) samples per geometry; idx_out [n_geom][m] int64 indices
+ * into the FLATTENED point array (g*n + i), in selection order.  Squared distances are
+ * accumulated left to right in fp32 without FMA contraction; ties -> lowest index (bit-exact
+ * against oracle/pyg_restate.py).
+ */
+int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m,
+             int64_t* idx_out, void* stream);
+
+/*
+ * Ball query, torch_cluster.radius(x=pos, y=pos[idx], r, batch, batch[idx], K) as called at
+ * models/modules.py:321: for each centroid the first k points (ascending index) of the same
+ * geometry with squared distance < r*r (strict).  nbr [n_geom*m][k] int32 flattened point indices,
+ * -1 padded; count [n_geom*m].
+ */
+int pcfd_ball_query(const float* pos, const int64_t* centroid_idx, int32_t n_geom, int32_t n, int32_t dims,
+                    int32_t m, float r, int32_t k, int32_t* nbr, int32_t* count, void* stream);
+
+/*
+ * Edge slots of one SetAbstraction layer with PyG PointNetConv's self-loop rule on the flattened
+ * bipartite graph (models/modules.py:322-323): drop neighbours whose flattened point index equals
+ * the flattened centroid index, then append source point i -> centroid i.  slots [m_total][k+1].
+ */
+int pcfd_sa_edges(const int32_t* nbr, int64_t m_total, int32_t k, int64_t n_points_total,
+                  int32_t* slots, void* stream);
+/*
+ * Edge features (PointConvNext.message, models/modules.py:286-292):
+ *   ein[(i,s)] = [ x[j][0:f_in], pos[j] - pos[centroid_i] / r ],  j = slots[i][s]; zeros if empty.
+ */
+int pcfd_sa_gather(const float* x, int32_t ldx, int32_t f_in, const float* pos, int32_t dims,
+                   const int64_t* centroid_idx, const int32_t* slots, int64_t m_total, int32_t kp, float r,
+                   float* ein, int32_t ldein, void* stream);
+/* gx[j][0:f_in] += gein[(i,s)][0:f_in] for every valid slot (atomic adds; gx is accumulated). */
+int pcfd_sa_scatter_bwd(const float* gein, int32_t ldgein, const int32_t* slots, int64_t m_total, int32_t kp,
+                        int32_t f_in, float* gx, int32_t ldgx, void* stream);
+
+/*
+ * FoamData indexing folded into one gather (dataset/foam_data.py:36-61: label -> column slice,
+ * sub-domain -> torch.gather):  out[g*out_rows_per_geom + out_row_offset + i][out_col_offset + c]
+ *   = data[g][row_ids[g][i]][cols[c]].   row_ids NULL -> rows first_row .. first_row+n_sel-1.
+ * cols_host: up to 32 column indices, read on the host at call time.
+ */
+int pcfd_gather_cols(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                     const int64_t* row_ids, int64_t first_row, int64_t n_sel,
+                     const int32_t* cols_host, int32_t n_cols,
+                     float* out, int32_t ldout, int64_t out_rows_per_geom, int64_t out_row_offset,
+                     int32_t out_col_offset, void* stream);
+
+/* Seeds the input jet of the per-point path: plane 0 = coordinates, plane k = e_k, others 0.
+ * (enable_internal_autograd, models/model_base.py:56-66: the points become the autograd leaf.) */
+int pcfd_seed_jet(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                  const int64_t* row_ids, int64_t n_sel, const int32_t* coord_cols_host, int32_t dims,
+                  int32_t cj, float* zout, int64_t plane_stride, int32_t ldz, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused residual assembly + losses + their gradient (models/losses.py:149-319, :10-20, :55-56;
+ * models/model_base.py:191-212).
+ * ------------------------------------------------------------------------------------------ */
+enum { PCFD_LOSS_MANUFACTURED = 0, PCFD_LOSS_FIXED = 1, PCFD_LOSS_VARIABLE = 2 };
+enum { PCFD_LAP_REFERENCE = 0, PCFD_LAP_TRUE = 1 };
+#define PCFD_LOSS_OUT_FLOATS 48
+/* layout of `out`: [0..15] unscaled loss terms in the reference's order
+ * (continuity, momentum xD, boundary U xD, boundary p, [obs U xD, obs p]); [16..31] the same
+ * times the loss weights; [32] their sum; [33..35] MAE of U per component, [36] MAE of p
+ * (calculate_errors, models/model_base.py:168-180); [37] number of loss terms. */
+
+typedef struct pcfd_residual_params {
+  int32_t dims, loss_kind, lap_mode, enable_data_loss;
+  float nu, d, f;                 /* scalar Darcy / Forchheimer coefficients (manufactured, fixed) */
+  float c_std[3], u_std[3], u_mean[3], p_std, p_mean;
+  float d_min[3], d_range[3], f_min[3], f_range[3];
+  int32_t col_u[3], col_p, col_zone, col_d[3], col_f[3]; /* column indices into data */
+  float weights[16];              /* FixedLossScaler weights (all 1 if the model has no scaler) */
+} pcfd_residual_params_t;
+
+size_t pcfd_residual_workspace_bytes(int32_t n_geom, int64_t ni, int64_t nb, int64_t no);
+/*
+ * y_int: jets of the model output at the internal points [cj][n_geom*ni][ldy] (cj = 1+D for
+ * PCFD_LAP_REFERENCE, 1+2D for PCFD_LAP_TRUE); y_bnd: values at the boundary points
+ * [n_geom*nb][ldy].  Writes gy_int / gy_bnd (same shapes, overwritten) = d(sum of scaled
+ * losses)/dy, and `out` (PCFD_LOSS_OUT_FLOATS floats).  Row ids index data[g] (targets) and the
+ * prediction order (internal rows first, then boundary rows), as in the reference.
+ */
+int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                       const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                       const int64_t* obs_ids, int64_t no,
+                       const float* y_int, int64_t y_plane_stride, const float* y_bnd, int32_t ldy,
+                       const pcfd_residual_params_t* prm_host,
+                       float* gy_int, float* gy_bnd, float* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = 0 for i < n (graph-capturable memset of gradient buffers) */
+int pcfd_zero(float* p, int64_t n, void* stream);
+/* *seed_dev = mix(*seed_dev) : advances the dropout seed once per step without a host round trip */
+int pcfd_advance_seed(uint64_t* seed_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCFD_H_ */

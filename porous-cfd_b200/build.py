@@ -1,0 +1,71 @@
+"""Builds libpcfd_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python porous-cfd_b200/build.py [--force]
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libpcfd_sm100.so')
+STAMP = os.path.join(HERE, 'csrc', '.build_stamp')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
+         '--expt-relaxed-constexpr', '-Xptxas', '-v']
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def digest():
+    h = hashlib.sha256()
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh'))
+    files.append(os.path.join(os.path.dirname(HERE), 'include', 'pcfd.h'))
+    for f in files:
+        h.update(f.encode())
+        h.update(open(f, 'rb').read())
+    h.update(' '.join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    d = digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == d:
+        return LIB
+    defines = []
+    if os.path.exists(os.path.join(CSRC, 'jet_linear_tc.cu')):
+        defines.append('-DPCFD_HAVE_TC')
+    objs = []
+    procs = []
+    for src in sources():
+        obj = src[:-3] + '.o'
+        objs.append(obj)
+        cmd = [NVCC, *FLAGS, *defines, '-c', src, '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f'==> {os.path.basename(src)}\n{out}')
+        if p.returncode != 0:
+            sys.stderr.write('\n'.join(log))
+            raise RuntimeError(f'nvcc failed on {src}')
+    cmd = [NVCC, '-shared', '-o', LIB, *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError('link failed')
+    with open(os.path.join(HERE, 'csrc', 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    open(STAMP, 'w').write(d)
+    if verbose:
+        print('\n'.join(log))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

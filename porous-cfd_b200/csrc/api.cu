@@ -1,0 +1,102 @@
+// C-ABI entry points that dispatch between the jet-GEMM engines, plus version / device queries.
+#include "common.cuh"
+
+extern "C" {
+int pcfd_ffma_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
+                             const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
+                             int32_t, void*);
+int pcfd_ffma_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
+                                const pcfd_intrans_t*, float*, int64_t, int32_t, float*, int32_t, int32_t, int64_t,
+                                int64_t, int32_t, int32_t, void*);
+int pcfd_ffma_jet_linear_bwd_dw(const float*, int64_t, int32_t, const float*, int64_t, int32_t, const pcfd_intrans_t*,
+                                float*, int32_t, float*, float*, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
+                                void*, size_t, void*);
+#ifdef PCFD_HAVE_TC
+int pcfd_tc_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
+                           const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
+                           int32_t, void*);
+int pcfd_tc_supported_fwd(int32_t cj, int64_t rows, int32_t k, int32_t n, int32_t ldzin, int32_t ldw, int32_t ldzout);
+#endif
+}
+
+static int g_engine = 0;
+static int g_arch_checked = 0;
+
+static int ensure_arch() {
+  if (g_arch_checked) return PCFD_OK;
+  int rc = pcfd::check_sm100();
+  if (rc == PCFD_OK) g_arch_checked = 1;
+  return rc;
+}
+
+extern "C" int pcfd_abi_version(void) { return PCFD_ABI_VERSION; }
+
+extern "C" int pcfd_device_arch(int* cc_out_host) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PCFD_ERR_ARCH;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return PCFD_ERR_ARCH;
+  if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return PCFD_ERR_ARCH;
+  if (cc_out_host) *cc_out_host = major * 10 + minor;
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_set_gemm_engine(int engine) {
+#ifdef PCFD_HAVE_TC
+  if (engine != 0 && engine != 1) return PCFD_ERR_ARG;
+#else
+  if (engine != 0) return PCFD_ERR_ARG;
+#endif
+  g_engine = engine;
+  return PCFD_OK;
+}
+extern "C" int pcfd_get_gemm_engine(void) { return g_engine; }
+
+static inline bool bad_jet(int cj, int64_t rows, int k, int n) { return !pcfd::valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0; }
+
+extern "C" int pcfd_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t ldzin, const pcfd_intrans_t* tin,
+                                   const float* w, int32_t ldw, const float* bias, const float* cvec, int32_t ldcvec,
+                                   float* zout, int64_t zout_ps, int32_t ldzout, int32_t cj, int64_t rows,
+                                   int64_t rows_per_geom, int32_t k, int32_t n, void* stream) {
+  if (!zin || !w || !zout || bad_jet(cj, rows, k, n) || ldzin < k || ldw < k || ldzout < n) return PCFD_ERR_ARG;
+  if ((cvec || (tin && tin->escale)) && rows_per_geom <= 0) return PCFD_ERR_ARG;
+  if (tin && tin->drop_p > 0.f && !tin->seed_dev) return PCFD_ERR_ARG;
+  int rc = ensure_arch();
+  if (rc) return rc;
+#ifdef PCFD_HAVE_TC
+  if (g_engine == 1 && pcfd_tc_supported_fwd(cj, rows, k, n, ldzin, ldw, ldzout))
+    return pcfd_tc_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
+                                  rows_per_geom, k, n, stream);
+#endif
+  return pcfd_ffma_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
+                                  rows_per_geom, k, n, stream);
+}
+
+extern "C" int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* w,
+                                      int32_t ldw, const float* zin, int64_t zin_ps, int32_t ldzin,
+                                      const pcfd_intrans_t* tin, float* gzin, int64_t gzin_ps, int32_t ldgzin,
+                                      float* gescale, int32_t ldgescale, int32_t cj, int64_t rows,
+                                      int64_t rows_per_geom, int32_t k, int32_t n, void* stream) {
+  if (!gzout || !w || !zin || !gzin || bad_jet(cj, rows, k, n) || ldgzout < n || ldw < k || ldzin < k || ldgzin < k)
+    return PCFD_ERR_ARG;
+  if ((gescale || (tin && tin->escale)) && rows_per_geom <= 0) return PCFD_ERR_ARG;
+  if (tin && tin->drop_p > 0.f && !tin->seed_dev) return PCFD_ERR_ARG;
+  int rc = ensure_arch();
+  if (rc) return rc;
+  return pcfd_ffma_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
+                                     gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);
+}
+
+extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* zin,
+                                      int64_t zin_ps, int32_t ldzin, const pcfd_intrans_t* tin, float* gw, int32_t ldgw,
+                                      float* gbias, float* gcvec, int32_t ldgcvec, int32_t cj, int64_t rows,
+                                      int64_t rows_per_geom, int32_t k, int32_t n, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  if (!gzout || !zin || !workspace || bad_jet(cj, rows, k, n) || ldgzout < n || ldzin < k || (gw && ldgw < k))
+    return PCFD_ERR_ARG;
+  if (tin && tin->escale && rows_per_geom <= 0) return PCFD_ERR_ARG;
+  if (tin && tin->drop_p > 0.f && !tin->seed_dev) return PCFD_ERR_ARG;
+  int rc = ensure_arch();
+  if (rc) return rc;
+  return pcfd_ffma_jet_linear_bwd_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, gw, ldgw, gbias, gcvec, ldgcvec,
+                                     cj, rows, rows_per_geom, k, n, workspace, workspace_bytes, stream);
+}

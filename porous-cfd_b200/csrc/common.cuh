@@ -1,0 +1,196 @@
+// Shared device helpers for libpcfd_sm100: jet activation algebra, dropout hash, launch checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pcfd.h"
+
+#define PCFD_CHECK_LAUNCH()                                   \
+  do {                                                        \
+    cudaError_t e__ = cudaGetLastError();                     \
+    if (e__ != cudaSuccess) return PCFD_ERR_CUDA + (int)e__;  \
+  } while (0)
+
+namespace pcfd {
+
+// ---- jet layout: cj -> (spatial dims D, derivative order) ---------------------------------
+template <int CJ> struct JetShape;
+template <> struct JetShape<1> { static constexpr int D = 0, ORDER = 0; };
+template <> struct JetShape<3> { static constexpr int D = 2, ORDER = 1; };
+template <> struct JetShape<4> { static constexpr int D = 3, ORDER = 1; };
+template <> struct JetShape<5> { static constexpr int D = 2, ORDER = 2; };
+template <> struct JetShape<7> { static constexpr int D = 3, ORDER = 2; };
+
+__host__ __device__ inline bool valid_cj(int cj) { return cj == 1 || cj == 3 || cj == 4 || cj == 5 || cj == 7; }
+
+// ---- activation and its first three derivatives -------------------------------------------
+struct ActD { float f0, f1, f2, f3; };
+
+template <bool NEED3>
+__device__ __forceinline__ ActD act_derivs(int act, float z) {
+  ActD r;
+  if (act == PCFD_ACT_SILU) {
+    // silu(z) = z*s, s = sigmoid(z); t = s(1-s)
+    float s = 1.0f / (1.0f + expf(-z));
+    float t = s * (1.0f - s);
+    float q = 1.0f - 2.0f * s;
+    r.f0 = z * s;
+    r.f1 = s + z * t;
+    r.f2 = t * (2.0f + z * q);
+    r.f3 = NEED3 ? t * (q * (3.0f + z * q) - 2.0f * z * t) : 0.0f;
+  } else if (act == PCFD_ACT_TANH) {
+    float t = tanhf(z);
+    float d = 1.0f - t * t;
+    r.f0 = t;
+    r.f1 = d;
+    r.f2 = -2.0f * t * d;
+    r.f3 = NEED3 ? -2.0f * d * (1.0f - 3.0f * t * t) : 0.0f;
+  } else {
+    r.f0 = z; r.f1 = 1.0f; r.f2 = 0.0f; r.f3 = 0.0f;
+  }
+  return r;
+}
+
+__device__ __forceinline__ float act_value(int act, float z) {
+  if (act == PCFD_ACT_SILU) return z / (1.0f + expf(-z));
+  if (act == PCFD_ACT_TANH) return tanhf(z);
+  return z;
+}
+__device__ __forceinline__ float act_d1(int act, float z) {
+  if (act == PCFD_ACT_SILU) { float s = 1.0f / (1.0f + expf(-z)); return s + z * s * (1.0f - s); }
+  if (act == PCFD_ACT_TANH) { float t = tanhf(z); return 1.0f - t * t; }
+  return 1.0f;
+}
+
+// ---- dropout: counter-based hash of (seed, salt, row, col) --------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+// multiplier applied to element (row, col): 0 (dropped) or 1/(1-p)
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t salt, int64_t row, int col, float p, float inv_keep) {
+  uint32_t h = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + salt));
+  h = mix32(h ^ (uint32_t)row);
+  h = mix32(h + 0x9e3779b9U * (uint32_t)col + (uint32_t)((uint64_t)row >> 32));
+  // uniform in [0,1): keep when u >= p
+  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.0f;
+}
+
+// Device-side view of pcfd_intrans_t (copied by value into kernel parameters).
+struct InTrans {
+  int act;
+  int act_cols;        // resolved: number of leading columns the transform applies to
+  const float* escale;
+  int ldescale;
+  float drop_p;
+  float inv_keep;
+  const uint64_t* seed_dev;
+  uint32_t salt;
+};
+
+inline InTrans make_intrans(const pcfd_intrans_t* t, int k) {
+  InTrans r;
+  if (t == nullptr) {
+    r.act = PCFD_ACT_NONE; r.act_cols = k; r.escale = nullptr; r.ldescale = 0; r.drop_p = 0.f; r.inv_keep = 1.f;
+    r.seed_dev = nullptr; r.salt = 0;
+    return r;
+  }
+  r.act = t->act;
+  r.act_cols = (t->act_cols <= 0 || t->act_cols > k) ? k : t->act_cols;
+  r.escale = t->escale; r.ldescale = t->ldescale;
+  r.drop_p = t->drop_p;
+  r.inv_keep = t->drop_p > 0.f ? 1.0f / (1.0f - t->drop_p) : 1.0f;
+  r.seed_dev = t->seed_dev; r.salt = t->salt;
+  return r;
+}
+
+// scale s = dropout mask * escale for input element (row, col); `m` receives the mask part alone
+__device__ __forceinline__ float in_scale(const InTrans& t, uint64_t seed, int64_t row, int64_t geom, int col, float& m) {
+  m = 1.0f;
+  if (t.drop_p > 0.0f) m = dropout_scale(seed, t.salt, row, col, t.drop_p, t.inv_keep);
+  float s = m;
+  if (t.escale != nullptr) s *= __ldg(t.escale + geom * t.ldescale + col);
+  return s;
+}
+
+// Forward input transform of one element, all channels.  z[] holds the CJ pre-activation
+// channels on entry and the transformed channels on exit.
+template <int CJ>
+__device__ __forceinline__ void jet_act_fwd(int act, float s, float (&z)[CJ]) {
+  constexpr int D = JetShape<CJ>::D;
+  constexpr int ORDER = JetShape<CJ>::ORDER;
+  if (act == PCFD_ACT_NONE) {
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) z[c] *= s;
+    return;
+  }
+  ActD a = act_derivs<false>(act, z[0]);
+  z[0] = a.f0 * s;
+  if (ORDER >= 1) {
+    float f1s = a.f1 * s, f2s = a.f2 * s;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float zk = z[1 + k];
+      if (ORDER >= 2) z[1 + D + k] = f2s * zk * zk + f1s * z[1 + D + k];
+      z[1 + k] = f1s * zk;
+    }
+  }
+}
+
+// Reverse of jet_act_fwd.  On entry g[] = gradient wrt the transformed channels, z[] = the
+// pre-activation channels.  On exit g[] = gradient wrt z[].  Returns sum_c g_in[c] * (a[c]/escale)
+// (the contribution to the escale gradient) where m is the dropout part of s.
+template <int CJ>
+__device__ __forceinline__ float jet_act_bwd(int act, float s, float m, const float (&z)[CJ], float (&g)[CJ]) {
+  constexpr int D = JetShape<CJ>::D;
+  constexpr int ORDER = JetShape<CJ>::ORDER;
+  float ge = 0.0f;
+  if (act == PCFD_ACT_NONE) {
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) { ge += g[c] * z[c] * m; g[c] *= s; }
+    return ge;
+  }
+  ActD a = act_derivs<(ORDER >= 2)>(act, z[0]);
+  ge = g[0] * a.f0;
+  float g0 = g[0] * s * a.f1;
+  if (ORDER >= 1) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      float zk = z[1 + k];
+      float gk = g[1 + k];
+      ge += gk * a.f1 * zk;
+      float gks = gk * s;
+      g0 += gks * a.f2 * zk;
+      float gzk = gks * a.f1;
+      if (ORDER >= 2) {
+        float zkk = z[1 + D + k];
+        float gkk = g[1 + D + k];
+        ge += gkk * (a.f2 * zk * zk + a.f1 * zkk);
+        float gkks = gkk * s;
+        g0 += gkks * (a.f3 * zk * zk + a.f2 * zkk);
+        gzk += gkks * 2.0f * a.f2 * zk;
+        g[1 + D + k] = gkks * a.f1;
+      }
+      g[1 + k] = gzk;
+    }
+  }
+  g[0] = g0;
+  return ge * m;
+}
+
+inline int check_sm100() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PCFD_ERR_ARCH;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return PCFD_ERR_ARCH;
+  return major == 10 ? PCFD_OK : PCFD_ERR_ARCH;
+}
+
+}  // namespace pcfd

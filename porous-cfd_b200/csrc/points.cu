@@ -1,0 +1,296 @@
+// Point-set kernels of the PointNet++ set abstraction (farthest point sampling, ball query, edge
+// gather / scatter) and the FoamData gathers.  Index results are bit-exact against
+// oracle/pyg_restate.py: squared distances use separately rounded fp32 multiplies and adds in
+// coordinate order (no FMA contraction), ties resolve to the lowest index.
+#include "common.cuh"
+
+namespace pcfd {
+
+template <int DIMS>
+__device__ __forceinline__ float sqdist(const float* __restrict__ p, const float* __restrict__ c) {
+  float d0 = __fsub_rn(p[0], c[0]);
+  float acc = __fmul_rn(d0, d0);
+#pragma unroll
+  for (int d = 1; d < DIMS; ++d) {
+    float dd = __fsub_rn(p[d], c[d]);
+    acc = __fadd_rn(acc, __fmul_rn(dd, dd));
+  }
+  return acc;
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  return v;
+}
+
+// One CTA per geometry.  Coordinates and running min-distances live in shared memory; one barrier
+// per sample: warps publish their best (distance, index) key into a double-buffered slot array and
+// every warp re-reduces the slots, so no second barrier is needed to broadcast the winner.
+template <int DIMS>
+__global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ pos, int n, int m,
+                                                   int64_t* __restrict__ idx_out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem;                 // [n][DIMS]
+  float* sd = smem + (size_t)n * DIMS;  // [n]
+  __shared__ unsigned long long slot[2][32];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const float* gp = pos + (size_t)g * n * DIMS;
+  for (int i = tid; i < n * DIMS; i += nt) sp[i] = gp[i];
+  __syncthreads();
+
+  int cur = 0;
+  if (tid == 0) idx_out[(size_t)g * m] = (int64_t)g * n;
+  for (int s = 1; s < m; ++s) {
+    float c[DIMS];
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) c[d] = sp[cur * DIMS + d];
+    unsigned long long best = 0ULL;
+    for (int p = tid; p < n; p += nt) {
+      float d = sqdist<DIMS>(sp + p * DIMS, c);
+      if (s > 1) d = fminf(sd[p], d);
+      sd[p] = d;
+      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(0xffffffffu - (unsigned)p);
+      best = key > best ? key : best;
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) slot[s & 1][warp] = best;
+    __syncthreads();
+    unsigned long long v = lane < nwarps ? slot[s & 1][lane] : 0ULL;
+    v = warp_max_u64(v);
+    cur = (int)(0xffffffffu - (unsigned)(v & 0xffffffffu));
+    if (tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + cur;
+  }
+}
+
+// One warp per centroid: scan the geometry's points 32 at a time, keep the first k hits by index.
+template <int DIMS>
+__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ pos,
+                                                         const int64_t* __restrict__ cidx, int n_geom, int n,
+                                                         int m, float r2, int k, int32_t* __restrict__ nbr,
+                                                         int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= (int64_t)n_geom * m) return;
+  const int g = (int)(q / m);
+  float c[DIMS];
+  const int64_t ci = cidx[q];
+#pragma unroll
+  for (int d = 0; d < DIMS; ++d) c[d] = __ldg(pos + ci * DIMS + d);
+  const float* gp = pos + (size_t)g * n * DIMS;
+  int found = 0;
+  for (int base = 0; base < n && found < k; base += 32) {
+    const int p = base + lane;
+    bool hit = false;
+    if (p < n) {
+      float pp[DIMS];
+#pragma unroll
+      for (int d = 0; d < DIMS; ++d) pp[d] = __ldg(gp + (size_t)p * DIMS + d);
+      hit = sqdist<DIMS>(pp, c) < r2;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    const int rank = found + __popc(mask & ((1u << lane) - 1u));
+    if (hit && rank < k) nbr[q * k + rank] = g * n + p;
+    found += __popc(mask);
+  }
+  if (found > k) found = k;
+  for (int j = found + lane; j < k; j += 32) nbr[q * k + j] = -1;
+  if (lane == 0 && count != nullptr) count[q] = found;
+}
+
+__global__ void sa_edges_kernel(const int32_t* __restrict__ nbr, int64_t m_total, int k, int64_t n_points_total,
+                                int32_t* __restrict__ slots) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_total) return;
+  const int kp = k + 1;
+  int w = 0;
+  for (int j = 0; j < k; ++j) {
+    const int v = nbr[i * k + j];
+    if (v >= 0 && (int64_t)v != i) slots[i * kp + w++] = v;   // remove_self_loops: numerically equal indices
+  }
+  if (i < n_points_total) slots[i * kp + w++] = (int32_t)i;    // add_self_loops(num_nodes = min(n_src, n_dst))
+  for (; w < kp; ++w) slots[i * kp + w] = -1;
+}
+
+__global__ void sa_gather_kernel(const float* __restrict__ x, int ldx, int f_in, const float* __restrict__ pos,
+                                 int dims, const int64_t* __restrict__ cidx, const int32_t* __restrict__ slots,
+                                 int64_t n_edges, int kp, float r, float* __restrict__ ein, int ldein) {
+  const int width = f_in + dims;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_edges * width) return;
+  const int64_t e = t / width;
+  const int col = (int)(t % width);
+  const int j = slots[e];
+  float v = 0.0f;
+  if (j >= 0) {
+    if (col < f_in) {
+      v = __ldg(x + (int64_t)j * ldx + col);
+    } else {
+      const int d = col - f_in;
+      const int64_t ci = cidx[e / kp];
+      // reference operator precedence: pos_j - (pos_i / r)   (models/modules.py:287)
+      v = __fsub_rn(__ldg(pos + (int64_t)j * dims + d), __fdiv_rn(__ldg(pos + ci * dims + d), r));
+    }
+  }
+  ein[e * ldein + col] = v;
+}
+
+__global__ void sa_scatter_bwd_kernel(const float* __restrict__ gein, int ldgein, const int32_t* __restrict__ slots,
+                                      int64_t n_edges, int f_in, float* gx, int ldgx) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_edges * f_in) return;
+  const int64_t e = t / f_in;
+  const int col = (int)(t % f_in);
+  const int j = slots[e];
+  if (j >= 0) atomicAdd(gx + (int64_t)j * ldgx + col, gein[e * ldgein + col]);
+}
+
+struct ColList { int32_t c[32]; };
+
+__global__ void gather_cols_kernel(const float* __restrict__ data, int64_t n_rows, int f,
+                                   const int64_t* __restrict__ row_ids, int64_t first_row, int64_t n_sel,
+                                   ColList cols, int n_cols, int64_t total, float* __restrict__ out, int ldout,
+                                   int64_t out_rows_per_geom, int64_t out_row_offset, int out_col_offset) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % n_cols);
+  const int64_t gi = t / n_cols;
+  const int64_t i = gi % n_sel, g = gi / n_sel;
+  const int64_t src_row = row_ids != nullptr ? row_ids[g * n_sel + i] : first_row + i;
+  out[(g * out_rows_per_geom + out_row_offset + i) * ldout + out_col_offset + c] =
+      __ldg(data + (g * n_rows + src_row) * f + cols.c[c]);
+}
+
+__global__ void seed_jet_kernel(const float* __restrict__ data, int64_t n_rows, int f,
+                                const int64_t* __restrict__ row_ids, int64_t n_sel, ColList cols, int dims, int cj,
+                                int64_t total, float* __restrict__ z, int64_t ps, int ldz) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t i = t % n_sel, g = t / n_sel;
+  const int64_t src_row = row_ids != nullptr ? row_ids[g * n_sel + i] : i;
+  for (int d = 0; d < dims; ++d) {
+    z[t * ldz + d] = __ldg(data + (g * n_rows + src_row) * f + cols.c[d]);
+    for (int c = 1; c < cj; ++c) z[c * ps + t * ldz + d] = (c == 1 + d) ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void advance_seed_kernel(uint64_t* seed) { *seed = mix64(*seed); }
+
+}  // namespace pcfd
+
+using namespace pcfd;
+
+extern "C" int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
+                        void* stream) {
+  if (!pos || !idx_out || n_geom <= 0 || n <= 0 || m <= 0 || m > n || (dims != 2 && dims != 3)) return PCFD_ERR_ARG;
+  const size_t smem = (size_t)n * (dims + 1) * sizeof(float);
+  if (smem > 220 * 1024) return PCFD_ERR_ARG;   // larger point sets need the clustered variant (not built yet)
+  int threads = n <= 1024 ? 256 : (n <= 4096 ? 512 : 1024);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (dims == 2) {
+    e = cudaFuncSetAttribute(fps_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+    fps_kernel<2><<<n_geom, threads, smem, st>>>(pos, n, m, idx_out);
+  } else {
+    e = cudaFuncSetAttribute(fps_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+    fps_kernel<3><<<n_geom, threads, smem, st>>>(pos, n, m, idx_out);
+  }
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_ball_query(const float* pos, const int64_t* centroid_idx, int32_t n_geom, int32_t n, int32_t dims,
+                               int32_t m, float r, int32_t k, int32_t* nbr, int32_t* count, void* stream) {
+  if (!pos || !centroid_idx || !nbr || n_geom <= 0 || n <= 0 || m <= 0 || k <= 0 || (dims != 2 && dims != 3))
+    return PCFD_ERR_ARG;
+  const int64_t q = (int64_t)n_geom * m;
+  const unsigned blocks = (unsigned)((q + 7) / 8);
+  const float r2 = r * r;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dims == 2) ball_query_kernel<2><<<blocks, 256, 0, st>>>(pos, centroid_idx, n_geom, n, m, r2, k, nbr, count);
+  else ball_query_kernel<3><<<blocks, 256, 0, st>>>(pos, centroid_idx, n_geom, n, m, r2, k, nbr, count);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_sa_edges(const int32_t* nbr, int64_t m_total, int32_t k, int64_t n_points_total, int32_t* slots,
+                             void* stream) {
+  if (!nbr || !slots || m_total <= 0 || k <= 0) return PCFD_ERR_ARG;
+  sa_edges_kernel<<<(unsigned)((m_total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(nbr, m_total, k, n_points_total, slots);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_sa_gather(const float* x, int32_t ldx, int32_t f_in, const float* pos, int32_t dims,
+                              const int64_t* centroid_idx, const int32_t* slots, int64_t m_total, int32_t kp, float r,
+                              float* ein, int32_t ldein, void* stream) {
+  if (!pos || !centroid_idx || !slots || !ein || m_total <= 0 || kp <= 0 || f_in < 0 || (f_in > 0 && !x))
+    return PCFD_ERR_ARG;
+  const int64_t total = m_total * kp * (f_in + dims);
+  sa_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, f_in, pos, dims, centroid_idx, slots, m_total * kp, kp, r, ein, ldein);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_sa_scatter_bwd(const float* gein, int32_t ldgein, const int32_t* slots, int64_t m_total,
+                                   int32_t kp, int32_t f_in, float* gx, int32_t ldgx, void* stream) {
+  if (!gein || !slots || !gx || m_total <= 0 || kp <= 0 || f_in <= 0) return PCFD_ERR_ARG;
+  const int64_t total = m_total * kp * f_in;
+  sa_scatter_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      gein, ldgein, slots, m_total * kp, f_in, gx, ldgx);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_gather_cols(const float* data, int32_t n_geom, int64_t n_rows, int32_t f, const int64_t* row_ids,
+                                int64_t first_row, int64_t n_sel, const int32_t* cols_host, int32_t n_cols,
+                                float* out, int32_t ldout, int64_t out_rows_per_geom, int64_t out_row_offset,
+                                int32_t out_col_offset, void* stream) {
+  if (!data || !out || !cols_host || n_cols <= 0 || n_cols > 32 || n_geom <= 0 || n_sel < 0) return PCFD_ERR_ARG;
+  if (n_sel == 0) return PCFD_OK;
+  ColList cl;
+  for (int i = 0; i < n_cols; ++i) {
+    if (cols_host[i] < 0 || cols_host[i] >= f) return PCFD_ERR_ARG;
+    cl.c[i] = cols_host[i];
+  }
+  const int64_t total = (int64_t)n_geom * n_sel * n_cols;
+  gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      data, n_rows, f, row_ids, first_row, n_sel, cl, n_cols, total, out, ldout, out_rows_per_geom, out_row_offset,
+      out_col_offset);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_seed_jet(const float* data, int32_t n_geom, int64_t n_rows, int32_t f, const int64_t* row_ids,
+                             int64_t n_sel, const int32_t* coord_cols_host, int32_t dims, int32_t cj, float* zout,
+                             int64_t plane_stride, int32_t ldz, void* stream) {
+  if (!data || !zout || !coord_cols_host || (dims != 2 && dims != 3) || !valid_cj(cj) || n_sel <= 0) return PCFD_ERR_ARG;
+  ColList cl;
+  for (int i = 0; i < dims; ++i) cl.c[i] = coord_cols_host[i];
+  const int64_t total = (int64_t)n_geom * n_sel;
+  seed_jet_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      data, n_rows, f, row_ids, n_sel, cl, dims, cj, total, zout, plane_stride, ldz);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_zero(float* p, int64_t n, void* stream) {
+  if (n <= 0) return PCFD_OK;
+  cudaError_t e = cudaMemsetAsync(p, 0, (size_t)n * sizeof(float), (cudaStream_t)stream);
+  return e == cudaSuccess ? PCFD_OK : PCFD_ERR_CUDA + (int)e;
+}
+
+extern "C" int pcfd_advance_seed(uint64_t* seed_dev, void* stream) {
+  if (!seed_dev) return PCFD_ERR_ARG;
+  advance_seed_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(seed_dev);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}

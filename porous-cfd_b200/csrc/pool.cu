@@ -1,0 +1,84 @@
+// Segmented max with arg-max (global max-pool of the PointNet encoders, max aggregation of the
+// set-abstraction convolution) and its backward scatter.  HBM-bound: every input element is read
+// once, coalesced along the feature axis; one CTA = 32 features x 8 row lanes of one segment.
+#include "common.cuh"
+
+namespace pcfd {
+
+__global__ void __launch_bounds__(256) segmax_fwd_kernel(const float* __restrict__ z, int ldz, int act,
+                                                         const int32_t* __restrict__ slots, int64_t n_seg,
+                                                         int seg_len, int c, float* __restrict__ out, int ldout,
+                                                         int32_t* __restrict__ arg) {
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + lane;
+  const int64_t seg = blockIdx.x;
+  float best = -INFINITY;
+  int besti = -1;
+  if (col < c) {
+    const float* base = z + seg * (int64_t)seg_len * ldz + col;
+    for (int j = wy; j < seg_len; j += 8) {
+      if (slots != nullptr && __ldg(slots + seg * seg_len + j) < 0) continue;
+      const float v = act_value(act, __ldg(base + (int64_t)j * ldz));
+      if (v > best || besti < 0) { best = v; besti = j; }   // strictly greater: first maximum wins inside a lane
+    }
+  }
+  sv[wy][lane] = best;
+  si[wy][lane] = besti;
+  __syncthreads();
+  if (wy == 0 && col < c) {
+    float b = sv[0][lane];
+    int bi = si[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float v = sv[i][lane];
+      const int vi = si[i][lane];
+      if (vi >= 0 && (bi < 0 || v > b || (v == b && vi < bi))) { b = v; bi = vi; }
+    }
+    out[seg * ldout + col] = bi >= 0 ? b : 0.0f;
+    arg[seg * c + col] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(256) segmax_bwd_kernel(const float* __restrict__ gout, int ldgout,
+                                                         const int32_t* __restrict__ arg,
+                                                         const float* __restrict__ z, int ldz, int act,
+                                                         int64_t n_seg, int seg_len, int c,
+                                                         float* __restrict__ gz, int ldgz) {
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + lane;
+  const int64_t seg = blockIdx.x;
+  if (col >= c) return;
+  const int a = __ldg(arg + seg * c + col);
+  const float g = __ldg(gout + seg * ldgout + col);
+  for (int j = wy; j < seg_len; j += 8) {
+    const int64_t row = seg * (int64_t)seg_len + j;
+    float v = 0.0f;
+    if (j == a) v = g * act_d1(act, __ldg(z + row * ldz + col));
+    gz[row * ldgz + col] = v;
+  }
+}
+
+}  // namespace pcfd
+
+using namespace pcfd;
+
+extern "C" int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots, int64_t n_seg,
+                               int32_t seg_len, int32_t c, float* out, int32_t ldout, int32_t* arg, void* stream) {
+  if (!z || !out || !arg || n_seg <= 0 || seg_len <= 0 || c <= 0) return PCFD_ERR_ARG;
+  dim3 grid((unsigned)n_seg, (unsigned)((c + 31) / 32));
+  segmax_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t* arg, const float* z, int32_t ldz,
+                               int32_t act, int64_t n_seg, int32_t seg_len, int32_t c, float* gz, int32_t ldgz,
+                               void* stream) {
+  if (!gout || !arg || !z || !gz || n_seg <= 0 || seg_len <= 0 || c <= 0) return PCFD_ERR_ARG;
+  dim3 grid((unsigned)n_seg, (unsigned)((c + 31) / 32));
+  segmax_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, ldgout, arg, z, ldz, act, n_seg, seg_len, c, gz, ldgz);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}

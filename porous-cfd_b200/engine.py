@@ -1,0 +1,442 @@
+"""Host-side executor of the fused physics-informed training step.
+
+It replaces the body of the reference's `PorousPinnBase.training_step`
+(models/model_base.py:182-218: forward, 1 + D + D*D + 1 reverse sweeps, residual losses, double
+backward) by ONE forward-mode jet pass through the shared per-point MLP stack, one fused residual
+kernel and one reverse pass, all of it C-ABI calls into libpcfd_sm100.so on the current CUDA
+stream (graph-capturable).  Python only sequences the calls and owns the buffers.
+
+Structure of a step:
+  encode      per-geometry constants: pooled global feature (MLP+max or set-abstraction stack),
+              branch embedding; folded into a per-geometry vector `cvec` added by the first layer
+              that consumes the concat [per-point features, global feature]
+  point chain jet pass on the internal points (cj = 1+D or 1+2D channels) and value pass on the
+              boundary points (cj = 1) through the same weights
+  residual    continuity / momentum / boundary / observation losses and d loss / d jet
+  backward    reverse chain (dX, dW), reverse encode
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib, ops
+from .ops import Jet
+
+
+@dataclass
+class ChainLayer:
+    weight: nn.Parameter
+    bias: Optional[nn.Parameter]
+    col_lo: int
+    k: int
+    n: int
+    act: Optional[str] = None        # transform applied to this layer's INPUT while it is loaded
+    act_cols: int = 0
+    drop_p: float = 0.0
+    escale: bool = False
+    cvec_key: Optional[str] = None   # per-geometry constant (bias folded into it) added to channel 0
+
+
+def mlp_chain(linears, act: str, last_activation: bool, dropout=None, first_act: Optional[str] = None,
+              first_drop: float = 0.0):
+    """Chain of a Linear->act(->Dropout) stack.  Activation/dropout of layer i are applied by
+    layer i+1 on load; returns (layers, pending) where pending = (act, drop_p) still to be applied
+    to the output of the last layer by whoever consumes it."""
+    layers = []
+    pend_act, pend_drop = first_act, first_drop
+    n_lin = len(linears)
+    for i, lin in enumerate(linears):
+        layers.append(ChainLayer(lin.weight, lin.bias, 0, lin.in_features, lin.out_features, act=pend_act,
+                                 drop_p=pend_drop))
+        pend_act = act if (i < n_lin - 1 or last_activation) else None
+        pend_drop = float(dropout[i]) if dropout is not None else 0.0
+    return layers, (pend_act, pend_drop)
+
+
+class StepContext:
+    """Buffers shared by the calls of one executor: gradient views, scratch workspace, dropout seed."""
+
+    def __init__(self, device):
+        self.device = device
+        self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.training = False
+        self.grads: dict[int, Tensor] = {}
+        self.salt = 0
+
+    def need_workspace(self, nbytes: int):
+        if self.workspace.numel() < nbytes:
+            self.workspace = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+
+    def grad(self, p: Optional[nn.Parameter]) -> Optional[Tensor]:
+        return None if p is None else self.grads[id(p)]
+
+
+def _tin(ctx: StepContext, layer: ChainLayer, escale: Optional[Tensor], salt: int):
+    drop = layer.drop_p if ctx.training else 0.0
+    if layer.act is None and drop == 0.0 and not layer.escale:
+        return None
+    return ops.make_intrans(layer.act, layer.act_cols, escale if layer.escale else None, drop, ctx.seed_dev, salt)
+
+
+def chain_forward(ctx: StepContext, layers, z0: Jet, rows_per_geom: int, escale: Optional[Tensor] = None,
+                  cvecs: Optional[dict] = None, salt_base: int = 0):
+    zs = [z0]
+    for i, L in enumerate(layers):
+        tin = _tin(ctx, L, escale, salt_base + i)
+        cvec = cvecs[L.cvec_key] if L.cvec_key is not None else None
+        bias = None if L.cvec_key is not None else L.bias
+        zs.append(ops.jet_linear_fwd(zs[-1], tin, L.weight, L.col_lo, L.k, bias, cvec, rows_per_geom, L.n))
+    return zs
+
+
+def chain_backward(ctx: StepContext, layers, zs, gz: Jet, rows_per_geom: int, escale: Optional[Tensor] = None,
+                   gescale: Optional[Tensor] = None, gcvecs: Optional[dict] = None, need_input_grad: bool = False,
+                   salt_base: int = 0) -> Optional[Jet]:
+    for i in range(len(layers) - 1, -1, -1):
+        L = layers[i]
+        zin = zs[i]
+        tin = _tin(ctx, L, escale, salt_base + i)
+        nbytes = ops.dw_workspace_bytes(zin.cj, zin.rows, rows_per_geom, L.k, L.n)
+        ctx.need_workspace(nbytes)
+        gbias = ctx.grad(L.bias) if L.cvec_key is None else None
+        gcvec = gcvecs[L.cvec_key] if L.cvec_key is not None else None
+        ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
+                              ctx.workspace)
+        if i > 0 or need_input_grad:
+            gz = ops.jet_linear_bwd_dx(gz, L.weight, L.col_lo, zin, tin, gescale if L.escale else None, rows_per_geom,
+                                       L.k, L.n)
+    return gz if need_input_grad else None
+
+
+# ------------------------------------------------------------------------------------------------
+# set-abstraction stack (models/modules.py:94-98, 295-325, 403-423, 483-527)
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class SALevel:
+    ratio: float
+    radius: float
+    layers: list
+    act: str
+    max_neighbors: int
+
+
+@dataclass
+class SAStack:
+    levels: list
+    global_layers: Optional[list]
+    act: str
+    out_features: int = 0
+
+
+def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int, pos0: Tensor):
+    """x0 [B*n0, ldx0] features, pos0 (B, n0, D) -> (g [B, ld] pooled feature, saved state)."""
+    b, n, d = pos0.shape
+    x, ldx, f, pos = x0, ldx0, f0, pos0
+    saved = {'levels': [], 'b': b, 'd': d}
+    for lvl in stack.levels:
+        idx = ops.fps(pos, lvl.ratio)
+        m = idx.shape[1]
+        nbr, _ = ops.ball_query(pos, idx, lvl.radius, lvl.max_neighbors)
+        slots = ops.sa_edges(nbr, b * n)
+        ein = ops.sa_gather(x, ldx, f, pos, idx, slots, lvl.radius)
+        zs = chain_forward(ctx, lvl.layers, Jet(ein, f + d), 0)
+        c = lvl.layers[-1].n
+        out, arg = ops.segmax_fwd(zs[-1].t[0], lvl.act, slots, b * m, slots.shape[1], c)
+        newpos = torch.empty((b, m, d), dtype=torch.float32, device=pos.device)
+        ops.gather_cols(pos, 1, b * n, d, idx, 0, b * m, list(range(d)), newpos, d, b * m)
+        saved['levels'].append({'slots': slots, 'zs': zs, 'arg': arg, 'm': m, 'n': n, 'f_in': f, 'ldx': ldx, 'c': c})
+        x, ldx, f, pos, n = out, out.stride(0), c, newpos, m
+    if stack.global_layers is None:
+        raise NotImplementedError('a set-abstraction stack without a final GlobalSetAbstraction is not used by any '
+                                  'in-scope model')
+    gin = torch.empty((1, b * n, ops.round4(f + d)), dtype=torch.float32, device=pos.device)
+    ops.gather_cols(x, 1, b * n, ldx, None, 0, b * n, list(range(f)), gin, gin.stride(1), b * n, 0, 0)
+    ops.gather_cols(pos, 1, b * n, d, None, 0, b * n, list(range(d)), gin, gin.stride(1), b * n, 0, f)
+    zs = chain_forward(ctx, stack.global_layers, Jet(gin, f + d), n)
+    e = stack.global_layers[-1].n
+    g, arg = ops.segmax_fwd(zs[-1].t[0], stack.act, None, b, n, e)
+    saved.update({'g_zs': zs, 'g_arg': arg, 'g_n': n, 'g_f': f, 'e': e})
+    return g, saved
+
+
+def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg: int) -> None:
+    b, n, e = saved['b'], saved['g_n'], saved['e']
+    zs = saved['g_zs']
+    gz = ops.segmax_bwd(gg, ldgg, saved['g_arg'], zs[-1].t[0], stack.act, b, n, e)
+    need = len(stack.levels) > 0
+    gin = chain_backward(ctx, stack.global_layers, zs, Jet(gz, e), n, need_input_grad=need)
+    if not need:
+        return
+    gx, ldgx = gin.t[0], gin.ld
+    for li in range(len(stack.levels) - 1, -1, -1):
+        lvl, sv = stack.levels[li], saved['levels'][li]
+        m_total = sv['slots'].shape[0]
+        zs = sv['zs']
+        gz = ops.segmax_bwd(gx, ldgx, sv['arg'], zs[-1].t[0], lvl.act, m_total, sv['slots'].shape[1], sv['c'])
+        gein = chain_backward(ctx, lvl.layers, zs, Jet(gz, sv['c']), 0, need_input_grad=(li > 0))
+        if li > 0:
+            gprev = torch.empty((b * sv['n'], sv['ldx']), dtype=torch.float32, device=gx.device)
+            ops.zero_(gprev)
+            ops.sa_scatter_bwd(gein.t[0], gein.ld, sv['slots'], sv['f_in'], gprev, sv['ldx'])
+            gx, ldgx = gprev, sv['ldx']
+
+
+# ------------------------------------------------------------------------------------------------
+# the step executor
+# ------------------------------------------------------------------------------------------------
+
+@dataclass
+class StepResult:
+    out: Tensor                # PCFD_LOSS_OUT_FLOATS device floats (see include/pcfd.h)
+    n_terms: int
+    y_int: Jet = None
+    y_bnd: Jet = None
+
+    @property
+    def loss(self) -> Tensor:
+        return self.out[32]
+
+    @property
+    def losses(self) -> Tensor:
+        return self.out[16:16 + self.n_terms]
+
+    @property
+    def unscaled(self) -> Tensor:
+        return self.out[0:self.n_terms]
+
+
+class PinnExecutor:
+    """Runs forward / training step of one model through the CUDA kernels.  Built lazily by
+    `PorousPinnBase` once the model lives on a CUDA device."""
+
+    def __init__(self, model):
+        self.model = model
+        self.device = next(model.parameters()).device
+        if self.device.type != 'cuda':
+            raise _lib.PcfdError('the porous-cfd hot path only runs on a CUDA sm_100 device; move the model with '
+                                 '.to("cuda") first (there is no CPU fallback)')
+        _lib.load()
+        self.ctx = StepContext(self.device)
+        self.params = [p for p in model.parameters()]
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.PcfdError('parameters must be contiguous float32')
+            self.ctx.grads[id(p)] = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.plan = model.build_plan()   # dict, see models/*.py
+
+    # ---- helpers --------------------------------------------------------------------------
+    def _cols(self, labels: dict, name: str):
+        keys = list(labels.keys())
+        sub = labels[name]
+        return [keys.index(s) for s in sub] if sub else [keys.index(name)]
+
+    def _gather(self, data: Tensor, row_ids: Optional[Tensor], n_sel: int, cols, out: Tensor, ldout: int,
+                out_rows_per_geom: int, out_row_offset: int = 0, out_col_offset: int = 0):
+        b, n_rows, f = data.shape
+        ops.gather_cols(data, b, n_rows, f, row_ids, 0, n_sel, cols, out, ldout, out_rows_per_geom, out_row_offset,
+                        out_col_offset)
+
+    def _segmax_features(self, ctx, layers, pending_act, zin: Jet, n_seg: int, seg_len: int):
+        zs = chain_forward(ctx, layers, zin, seg_len)
+        c = layers[-1].n
+        out, arg = ops.segmax_fwd(zs[-1].t[0], pending_act, None, n_seg, seg_len, c)
+        return out, {'zs': zs, 'arg': arg, 'n_seg': n_seg, 'seg_len': seg_len, 'c': c, 'act': pending_act}
+
+    def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False):
+        gz = ops.segmax_bwd(gout, ldgout, sv['arg'], sv['zs'][-1].t[0], sv['act'], sv['n_seg'], sv['seg_len'], sv['c'])
+        return chain_backward(ctx, layers, sv['zs'], Jet(gz, sv['c']), sv['seg_len'], need_input_grad=need_input_grad)
+
+    # ---- encode: per-geometry constants ------------------------------------------------------
+    def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor]):
+        """Returns (cvecs, escale, saved).  `points` (B,N,D) overrides the coordinates taken from
+        `data` (used by forward(autograd_points, x))."""
+        plan, ctx = self.plan, self.ctx
+        b, n_rows, f = data.shape
+        d = plan['dims']
+        c_cols = self._cols(labels, 'C')
+        saved = {}
+        cvecs, escale = {}, None
+        fam = plan['family']
+        if fam in ('pipn_pp', 'pigano_pp'):
+            bnd_ids = domain['boundary']
+            nb = bnd_ids.shape[1]
+            pos = torch.empty((b, nb, d), dtype=torch.float32, device=data.device)
+            self._gather(data, bnd_ids, nb, c_cols, pos, d, nb)
+            gcols = []
+            for name in plan['geom_feature_order']:
+                gcols += self._cols(labels, name)
+            x0 = torch.empty((b * nb, ops.round4(len(gcols))), dtype=torch.float32, device=data.device)
+            self._gather(data, bnd_ids, nb, gcols, x0, x0.stride(0), nb)
+            g, sa_saved = sa_forward(ctx, plan['sa_stack'], x0, x0.stride(0), len(gcols), pos)
+            saved['sa'] = sa_saved
+            gfeat, gwidth = g, plan['sa_stack'].global_layers[-1].n
+        elif fam == 'pigano':
+            n_all = n_rows
+            gcols = self._cols(labels, 'boundaryId') + self._cols(labels, 'sdf')
+            width = len(gcols) + d
+            gin = torch.empty((1, b * n_all, ops.round4(width)), dtype=torch.float32, device=data.device)
+            self._gather(data, None, n_all, gcols, gin, gin.stride(1), n_all)
+            if points is not None:
+                ops.gather_cols(points, b, n_all, d, None, 0, n_all, list(range(d)), gin, gin.stride(1), n_all, 0,
+                                len(gcols))
+            else:
+                ni, nbd = pts_int_ids.shape[1], pts_bnd_ids.shape[1]
+                self._gather(data, pts_int_ids, ni, c_cols, gin, gin.stride(1), n_all, 0, len(gcols))
+                self._gather(data, pts_bnd_ids, nbd, c_cols, gin, gin.stride(1), n_all, ni, len(gcols))
+            gfeat, saved['geom'] = self._segmax_features(ctx, plan['geom_layers'], plan['geom_pending_act'],
+                                                         Jet(gin, width), b, n_all)
+            gwidth = plan['geom_layers'][-1].n
+        elif fam == 'pipn':
+            gfeat, gwidth, saved['pipn'] = self._encode_pipn(data, labels, pts_int_ids, pts_bnd_ids, points)
+        else:
+            raise KeyError(fam)
+
+        if fam in ('pigano', 'pigano_pp'):
+            # branch network over (sub-domain rows x [C, variable-boundary features]) (models/pi_gano/base.py:60-73)
+            vb = plan['variable_boundaries']
+            pcols = list(c_cols)
+            for name in vb['Features']:
+                pcols += self._cols(labels, name)
+            counts = [domain[s].shape[1] for s in vb['Subdomains']]
+            n_par = sum(counts)
+            pin = torch.empty((1, b * n_par, ops.round4(len(pcols))), dtype=torch.float32, device=data.device)
+            off = 0
+            for s, cnt in zip(vb['Subdomains'], counts):
+                self._gather(data, domain[s], cnt, pcols, pin, pin.stride(1), n_par, off)
+                off += cnt
+            escale, saved['branch'] = self._segmax_features(ctx, plan['branch_layers'], plan['branch_pending_act'],
+                                                            Jet(pin, len(pcols)), b, n_par)
+
+        # fold the global feature into the per-geometry constant of the concat layer
+        cl = plan['concat_layer']            # ChainLayer over the GLOBAL column block (bias lives here)
+        gjet = Jet(gfeat.unsqueeze(0), gwidth)
+        cv = ops.jet_linear_fwd(gjet, None, cl.weight, cl.col_lo, cl.k, cl.bias, None, 0, cl.n)
+        cvecs['concat'] = cv.t[0]
+        saved['gjet'] = gjet
+        return cvecs, escale, saved
+
+    def _encode_pipn(self, data, labels, pts_int_ids, pts_bnd_ids, points):
+        """Vanilla PIPN global feature (models/modules.py:71-82): local MLP on every point, concat with
+        [boundaryId, sdf], global MLP, max over points.  Value path only: the dependence of the pooled
+        feature on the autograd points (max-pool coupling) is NOT carried in
+        the tangents."""
+        plan, ctx = self.plan, self.ctx
+        b, n_rows, f = data.shape
+        d = plan['dims']
+        c_cols = self._cols(labels, 'C')
+        z0 = Jet.empty(1, b * n_rows, d, data.device)
+        if points is not None:
+            ops.gather_cols(points, b, n_rows, d, None, 0, n_rows, list(range(d)), z0.t, z0.ld, n_rows)
+        else:
+            ni, nbd = pts_int_ids.shape[1], pts_bnd_ids.shape[1]
+            self._gather(data, pts_int_ids, ni, c_cols, z0.t, z0.ld, n_rows, 0)
+            self._gather(data, pts_bnd_ids, nbd, c_cols, z0.t, z0.ld, n_rows, ni)
+        zs_local = chain_forward(ctx, plan['local_layers'], z0, n_rows)
+        lw = plan['local_layers'][-1].n
+        gcols = self._cols(labels, 'boundaryId') + self._cols(labels, 'sdf')
+        width = lw + len(gcols)
+        gin = Jet.empty(1, b * n_rows, width, data.device)
+        ops.gather_cols(zs_local[-1].t, 1, b * n_rows, zs_local[-1].ld, None, 0, b * n_rows, list(range(lw)),
+                        gin.t, gin.ld, b * n_rows)
+        self._gather(data, None, n_rows, gcols, gin.t, gin.ld, n_rows, 0, lw)
+        gfeat, sv = self._segmax_features(ctx, plan['global_layers'], plan['global_pending_act'], gin, b, n_rows)
+        return gfeat, plan['global_layers'][-1].n, {'zs_local': zs_local, 'global': sv, 'lw': lw}
+
+    def _encode_backward(self, saved: dict, gcvecs: dict, gescale: Optional[Tensor]):
+        plan, ctx = self.plan, self.ctx
+        cl = plan['concat_layer']
+        gjet = saved['gjet']
+        gcv = Jet(gcvecs['concat'].unsqueeze(0), cl.n)
+        ctx.need_workspace(ops.dw_workspace_bytes(1, gjet.rows, 0, cl.k, cl.n))
+        ops.jet_linear_bwd_dw(gcv, gjet, None, ctx.grad(cl.weight), cl.col_lo, ctx.grad(cl.bias), None, 0, cl.k, cl.n,
+                              ctx.workspace)
+        gg = ops.jet_linear_bwd_dx(gcv, cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
+        fam = plan['family']
+        if fam in ('pipn_pp', 'pigano_pp'):
+            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld)
+        elif fam == 'pigano':
+            self._segmax_features_bwd(ctx, plan['geom_layers'], saved['geom'], gg.t[0], gg.ld)
+        elif fam == 'pipn':
+            sv = saved['pipn']
+            gin = self._segmax_features_bwd(ctx, plan['global_layers'], sv['global'], gg.t[0], gg.ld,
+                                            need_input_grad=True)
+            # gradient of the local features: first lw columns of the concat input, pending activation is
+            # applied by the global MLP's first layer (act_cols = lw), so gin[:, :lw] is d/d z_local
+            glocal = Jet(gin.t[:, :, :], sv['lw'])
+            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows)
+        if fam in ('pigano', 'pigano_pp'):
+            self._segmax_features_bwd(ctx, plan['branch_layers'], saved['branch'], gescale, gescale.stride(0))
+
+    # ---- public entry points -----------------------------------------------------------------
+    def forward_values(self, points: Tensor, data: Tensor, labels: dict, domain: dict) -> Tensor:
+        """Model.forward(autograd_points, x): predictions (B, N, D+1) at `points` (value pass only)."""
+        plan, ctx = self.plan, self.ctx
+        ctx.training = self.model.training
+        b, n, d = points.shape
+        points = points.detach().contiguous().float()
+        cvecs, escale, _ = self._encode(data, labels, domain, None, None, points)
+        z0 = Jet.empty(1, b * n, d, data.device)
+        ops.gather_cols(points, b, n, d, None, 0, n, list(range(d)), z0.t, z0.ld, n)
+        zs = chain_forward(ctx, plan['point_layers'], z0, n, escale, cvecs, salt_base=100)
+        return zs[-1].values().reshape(b, n, d + 1)
+
+    def step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
+             keep_outputs: bool = False) -> StepResult:
+        """One fused training step: fills the flat gradient buffer and returns the loss vector."""
+        plan, ctx = self.plan, self.ctx
+        model = self.model
+        ctx.training = model.training
+        if data.dtype != torch.float32 or not data.is_contiguous():
+            raise _lib.PcfdError('FoamData.data must be contiguous float32')
+        b, n_rows, f = data.shape
+        d = plan['dims']
+        int_ids, bnd_ids = domain['internal'], domain['boundary']
+        ni, nb = int_ids.shape[1], bnd_ids.shape[1]
+        obs_ids = domain.get('obs') if model.enable_data_loss else None
+        if obs_ids is not None and obs_ids.shape[1] == 0:
+            obs_ids = None
+        cj = 1 + d if laplacian == 'reference' else 1 + 2 * d
+        c_cols = self._cols(labels, 'C')
+
+        ops.zero_(self.flat_grad)
+        if ctx.training:
+            ops.advance_seed(ctx.seed_dev)
+
+        cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None)
+        z0_int = ops.seed_jet(data, int_ids, ni, c_cols, cj)
+        z0_bnd = ops.seed_jet(data, bnd_ids, nb, c_cols, 1)
+        layers = plan['point_layers']
+        zs_int = chain_forward(ctx, layers, z0_int, ni, escale, cvecs, salt_base=100)
+        zs_bnd = chain_forward(ctx, layers, z0_bnd, nb, escale, cvecs, salt_base=200)
+
+        prm = model.residual_params(labels, laplacian)
+        ctx.need_workspace(ops.residual_workspace_bytes(b, ni, nb, obs_ids.shape[1] if obs_ids is not None else 0))
+        gy_int, gy_bnd, out = ops.residual_loss(data, int_ids, bnd_ids, obs_ids, zs_int[-1], zs_bnd[-1], prm,
+                                                ctx.workspace)
+
+        gcvecs = {'concat': torch.empty_like(cvecs['concat'])}
+        ops.zero_(gcvecs['concat'])
+        gescale = None
+        if escale is not None:
+            gescale = torch.empty_like(escale)
+            ops.zero_(gescale)
+        chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100)
+        chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200)
+        self._encode_backward(saved, gcvecs, gescale)
+
+        n_terms = 2 * d + 2 + ((d + 1) if obs_ids is not None else 0)
+        res = StepResult(out, n_terms)
+        if keep_outputs:
+            res.y_int, res.y_bnd = zs_int[-1], zs_bnd[-1]
+        return res

@@ -1,0 +1,221 @@
+"""PorousPinnBase: the reference's training / validation / prediction seams
+(reference models/model_base.py:69-254) on top of the CUDA executor.
+
+`training_step(batch, batch_idx)` keeps its signature and returns a 0-d loss tensor whose
+`.backward()` delivers the parameter gradients, but the body is one fused step
+(engine.PinnExecutor.step): a forward-mode jet pass instead of the reference's 1 + D + D*D + 1
+autograd sweeps, one residual kernel, one reverse pass.  The gradients are computed in the step
+itself; `backward()` only scales them by the incoming gradient and hands them to autograd.
+
+`laplacian` selects the viscous operator:
+  'reference'  what training_step computes as written (`get_laplacian(points, U)`, :195)
+  'true'       the documented operator (`get_laplacian(points, get_jacobian(points, U))`)
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .. import _lib
+from .._lib import LAP_MODES, LOSS_KINDS, ResidualParams
+from ..dataset.foam_data import FoamData
+from ..engine import PinnExecutor
+from .losses import LossLogger
+
+try:  # a real LightningModule when lightning is installed, so Trainer.fit() accepts the model
+    import lightning as _L
+    _Base = _L.LightningModule
+except Exception:  # lightning is not part of this image: same surface on top of nn.Module
+    class _Base(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.logged: dict = {}
+            self.hparams_saved: dict = {}
+            self.global_step = 0
+
+        def save_hyperparameters(self, *args, **kwargs):
+            pass
+
+        def log(self, name, value, **kwargs):
+            self.logged[name] = value
+
+
+class _StepGradients(torch.autograd.Function):
+    """Connects the fused step to autograd: forward returns the loss computed by the kernels,
+    backward returns the gradients the same step already produced (scaled by grad_output)."""
+
+    @staticmethod
+    def forward(ctx, executor: PinnExecutor, loss: Tensor, *params):
+        ctx.executor = executor
+        return loss.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        ex = ctx.executor
+        scaled = ex.flat_grad * grad_out
+        grads, off = [], 0
+        for p in ex.params:
+            grads.append(scaled[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return (None, None, *grads)
+
+
+def calculate_gradients(outputs, inputs):
+    raise NotImplementedError('reverse-mode sweeps are replaced by the forward-mode jet pass; use '
+                              'PorousPinnBase.jets(batch) to obtain U, jacobian, laplacian and grad p')
+
+
+class PorousPinnBase(_Base):
+    def __init__(self, out_features: int, enable_data_loss=True, loss_scaler=None, laplacian: str = 'reference'):
+        super().__init__()
+        self.verbose_predict = False
+        self.enable_data_loss = bool(enable_data_loss)
+        self.dims = out_features - 1
+        self.laplacian = laplacian
+        n = out_features
+        physics = ['Continuity loss', 'Momentum x loss', 'Momentum y loss', 'Momentum z loss'][:n]
+        boundary = ['Boundary loss p', 'Boundary loss ux', 'Boundary loss uy', 'Boundary loss uz'][:n]
+        obs = ['Observations loss p', 'Observations loss ux', 'Observations loss uy',
+               'Observations loss uz'][:n] if self.enable_data_loss else []
+        errors = ['error p', 'error ux', 'error uy', 'error uz'][:n]
+        self.training_loss_togger = LossLogger(self, 'Total loss', *physics, *boundary, *obs,
+                                               *[f'Train {e}' for e in errors])
+        self.val_loss_logger = LossLogger(self, *[f'Validation {e}' for e in errors])
+        self.predicted_labels = self.get_predicted_labels()
+        self.extra_labels = self.get_extra_labels()
+        self.loss_scaler = loss_scaler
+        self._executor: Optional[PinnExecutor] = None
+        self._prm_cache: dict = {}
+        self.last_step = None
+
+    # ---- reference helpers ---------------------------------------------------------------------
+    def to(self, *args: Any, **kwargs: Any):
+        super().to(*args, **kwargs)
+        if self.loss_scaler is not None:
+            self.loss_scaler = self.loss_scaler.to(*args, **kwargs)
+        self._executor = None
+        return self
+
+    def get_predicted_labels(self) -> dict:
+        u = ['Ux', 'Uy', 'Uz'][:self.dims]
+        return {**dict.fromkeys(u), 'p': None, 'U': u}
+
+    def get_extra_labels(self) -> dict:
+        m = ['Momentumx', 'Momentumy', 'Momentumz'][:self.dims]
+        return {**dict.fromkeys(m), 'div': None, 'Momentum': m}
+
+    def postprocess_out(self, u: Tensor, p: Tensor):
+        return u, p
+
+    def transfer_batch_to_device(self, batch: FoamData, device, dataloader_idx: int = 0) -> FoamData:
+        return batch.to(device, non_blocking=True)
+
+    # ---- executor plumbing -----------------------------------------------------------------------
+    @property
+    def executor(self) -> PinnExecutor:
+        if self._executor is None:
+            self._executor = PinnExecutor(self)
+        return self._executor
+
+    def build_plan(self) -> dict:
+        raise NotImplementedError
+
+    def loss_spec(self) -> dict:
+        """{'kind', 'nu', 'd', 'f', scalers...} -- provided by the concrete model."""
+        raise NotImplementedError
+
+    def residual_params(self, labels: dict, laplacian: str) -> ResidualParams:
+        key = (tuple(labels), laplacian)
+        if key in self._prm_cache:
+            return self._prm_cache[key]
+        spec = self.loss_spec()
+        d = self.dims
+        keys = list(labels.keys())
+        col = lambda name: keys.index(name)
+        prm = ResidualParams()
+        prm.dims, prm.loss_kind, prm.lap_mode = d, LOSS_KINDS[spec['kind']], LAP_MODES[laplacian]
+        prm.enable_data_loss = 1 if self.enable_data_loss else 0
+        prm.nu, prm.d, prm.f = float(spec['nu']), float(spec.get('d', 0.0)), float(spec.get('f', 0.0))
+
+        def vec(x, n):
+            t = torch.as_tensor(x, dtype=torch.float64).flatten().cpu()
+            if t.numel() == 1:
+                t = t.repeat(n)
+            return [float(v) for v in t[:n]]
+
+        ones, zeros = [1.0] * 3, [0.0] * 3
+        if spec['kind'] != 'manufactured':
+            prm.c_std[:d], prm.u_std[:d], prm.u_mean[:d] = vec(spec['C'].std, d), vec(spec['U'].std, d), vec(spec['U'].mean, d)
+            prm.p_std, prm.p_mean = vec(spec['p'].std, 1)[0], vec(spec['p'].mean, 1)[0]
+        else:
+            prm.c_std[:], prm.u_std[:], prm.u_mean[:] = ones, ones, zeros
+            prm.p_std, prm.p_mean = 1.0, 0.0
+        if spec['kind'] == 'variable':
+            prm.d_min[:d], prm.d_range[:d] = vec(spec['d_scaler'].min, d), vec(spec['d_scaler'].range, d)
+            prm.f_min[:d], prm.f_range[:d] = vec(spec['f_scaler'].min, d), vec(spec['f_scaler'].range, d)
+        u_names = labels['U']
+        prm.col_u[:d] = [col(n) for n in u_names]
+        prm.col_p, prm.col_zone = col('p'), col('cellToRegion')
+        if spec['kind'] == 'variable':
+            prm.col_d[:d] = [col(n) for n in labels['d']]
+        if spec['kind'] in ('variable', 'manufactured'):
+            prm.col_f[:d] = [col(n) for n in labels['f']]
+        n_terms = 2 * d + 2 + ((d + 1) if self.enable_data_loss else 0)
+        w = self.loss_scaler.weights(n_terms) if self.loss_scaler is not None else [1.0] * n_terms
+        prm.weights[:] = (w + [0.0] * 16)[:16]
+        self._prm_cache[key] = prm
+        return prm
+
+    # ---- model API ----------------------------------------------------------------------------------
+    def forward(self, autograd_points: Tensor, x: FoamData) -> FoamData:
+        """Predictions at `autograd_points` (B, N, D): FoamData with columns [U..., p] and x's domain."""
+        y = self.executor.forward_values(autograd_points, x.data, x.labels, x.domain)
+        return FoamData(y, self.predicted_labels, x.domain)
+
+    def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False):
+        """The hot path without the autograd wrapper: fills `executor.flat_grad`, returns StepResult."""
+        return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs)
+
+    def training_step(self, batch: FoamData, batch_idx: int = 0):
+        res = self.fused_step(batch)
+        self.last_step = res
+        loss = _StepGradients.apply(self.executor, res.loss, *self.executor.params)
+        d = self.dims
+        out = res.out
+        self.training_loss_togger.log(len(batch.data), out[32], *out[16:16 + res.n_terms], out[36], *out[33:33 + d])
+        return loss
+
+    def validation_step(self, batch: FoamData, batch_idx: int = 0):
+        predicted = self.forward(batch['C'], batch)
+        u_error, p_error = self.calculate_errors(batch, predicted)
+        self.val_loss_logger.log(len(batch.data), p_error, *u_error)
+
+    def calculate_errors(self, target: FoamData, predicted: FoamData):
+        """MAE of de-standardised U (D,) and p (logging only; reference models/model_base.py:168-180)."""
+        pu, pp = self.postprocess_out(predicted['U'], predicted['p'])
+        tu, tp = self.postprocess_out(target['U'], target['p'])
+        return (pu - tu).abs().reshape(-1, pu.shape[-1]).mean(0), (pp - tp).abs().mean()
+
+    def predict_step(self, batch: FoamData, batch_idx: int = 0):
+        if self.verbose_predict:
+            raise NotImplementedError('residual fields at inference are a "next" row (SURVEY.md section 8f rank 3)')
+        return self.forward(batch['C'], batch)
+
+    def jets(self, batch: FoamData, laplacian: str = 'true') -> dict:
+        """U, p, jacobian, laplacian and grad p at the internal points from the forward-mode jet
+        (what get_jacobian / get_laplacian / calculate_gradients return in the reference)."""
+        res = self.fused_step(batch, laplacian, keep_outputs=True)
+        d = self.dims
+        y = res.y_int.t[:, :, :d + 1]
+        b = batch.data.shape[0]
+        ni = y.shape[1] // b
+        u, p = y[0, :, :d], y[0, :, d:]
+        jac = y[1:1 + d, :, :d].permute(1, 2, 0)          # [row, i, j] = dU_i/dx_j
+        dp = y[1:1 + d, :, d].permute(1, 0)
+        out = {'U': u.reshape(b, ni, d), 'p': p.reshape(b, ni, 1), 'jacobian': jac.reshape(b, ni, d, d),
+               'd_p': dp.reshape(b, ni, d)}
+        if laplacian == 'true':
+            out['laplacian'] = y[1 + d:1 + 2 * d, :, :d].permute(1, 2, 0).reshape(b, ni, d, d)
+        return out

@@ -1,0 +1,251 @@
+"""Tensor-level wrappers of the C ABI (include/pcfd.h).  Each function takes CUDA tensors, passes
+raw device pointers and the current torch stream to libpcfd_sm100.so and raises on a non-zero
+status.  No arithmetic happens in Python or in torch kernels here."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ACT_CODES, InTrans, ResidualParams, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise _lib.PcfdError(f'{name}: expected a CUDA float32 tensor, got {t.dtype} on {t.device}')
+    return t
+
+
+def round4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def make_intrans(act=None, act_cols: int = 0, escale: Optional[Tensor] = None, drop_p: float = 0.0,
+                 seed_dev: Optional[Tensor] = None, salt: int = 0) -> InTrans:
+    t = InTrans()
+    t.act = ACT_CODES[act] if not isinstance(act, int) else act
+    t.act_cols = act_cols
+    t.escale = _ptr(escale)
+    t.ldescale = escale.stride(0) if escale is not None else 0
+    t.drop_p = float(drop_p)
+    t.seed_dev = _ptr(seed_dev) if drop_p > 0 else None
+    t.salt = salt
+    return t
+
+
+class Jet:
+    """A jet tensor [cj][rows][ld] (ld = width rounded up to 4 floats for vector stores)."""
+    __slots__ = ('t', 'cj', 'rows', 'width')
+
+    def __init__(self, t: Tensor, width: int):
+        self.t, self.cj, self.rows, self.width = t, t.shape[0], t.shape[1], width
+
+    @staticmethod
+    def empty(cj: int, rows: int, width: int, device) -> 'Jet':
+        return Jet(torch.empty((cj, rows, round4(width)), dtype=torch.float32, device=device), width)
+
+    @property
+    def ld(self) -> int:
+        return self.t.stride(1)
+
+    @property
+    def plane_stride(self) -> int:
+        return self.t.stride(0)
+
+    def values(self) -> Tensor:
+        return self.t[0, :, :self.width]
+
+
+def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: int, bias: Optional[Tensor],
+                   cvec: Optional[Tensor], rows_per_geom: int, n: int, out: Optional[Jet] = None) -> Jet:
+    lib = _lib.load()
+    if out is None:
+        out = Jet.empty(zin.cj, zin.rows, n, zin.t.device)
+    _lib.launches += 1
+    check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
+                                  w.data_ptr() + 4 * col_lo, w.stride(0), _ptr(bias), _ptr(cvec),
+                                  cvec.stride(0) if cvec is not None else 0,
+                                  out.t.data_ptr(), out.plane_stride, out.ld, zin.cj, zin.rows, rows_per_geom, k, n,
+                                  _stream()), 'pcfd_jet_linear_fwd')
+    return out
+
+
+def jet_linear_bwd_dx(gzout: Jet, w: Tensor, col_lo: int, zin: Jet, tin: Optional[InTrans],
+                      gescale: Optional[Tensor], rows_per_geom: int, k: int, n: int) -> Jet:
+    lib = _lib.load()
+    gzin = Jet.empty(zin.cj, zin.rows, k, zin.t.device)
+    _lib.launches += 1
+    check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, w.data_ptr() + 4 * col_lo,
+                                     w.stride(0), zin.t.data_ptr(), zin.plane_stride, zin.ld,
+                                     C.byref(tin) if tin is not None else None,
+                                     gzin.t.data_ptr(), gzin.plane_stride, gzin.ld, _ptr(gescale),
+                                     gescale.stride(0) if gescale is not None else 0,
+                                     zin.cj, zin.rows, rows_per_geom, k, n, _stream()), 'pcfd_jet_linear_bwd_dx')
+    return gzin
+
+
+def dw_workspace_bytes(cj: int, rows: int, rows_per_geom: int, k: int, n: int) -> int:
+    return int(_lib.load().pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n))
+
+
+def jet_linear_bwd_dw(gzout: Jet, zin: Jet, tin: Optional[InTrans], gw: Optional[Tensor], col_lo: int,
+                      gbias: Optional[Tensor], gcvec: Optional[Tensor], rows_per_geom: int, k: int, n: int,
+                      workspace: Tensor) -> None:
+    lib = _lib.load()
+    _lib.launches += 2 + (2 if (gbias is not None or gcvec is not None) else 0)
+    check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
+                                     zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
+                                     (gw.data_ptr() + 4 * col_lo) if gw is not None else None,
+                                     gw.stride(0) if gw is not None else 0, _ptr(gbias), _ptr(gcvec),
+                                     gcvec.stride(0) if gcvec is not None else 0, zin.cj, zin.rows, rows_per_geom, k, n,
+                                     workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()),
+          'pcfd_jet_linear_bwd_dw')
+
+
+def segmax_fwd(z: Tensor, act, slots: Optional[Tensor], n_seg: int, seg_len: int, c: int):
+    """z [(n_seg*seg_len), ld] pre-activations -> (out [n_seg, c], arg [n_seg, c] int32)."""
+    lib = _lib.load()
+    out = torch.empty((n_seg, round4(c)), dtype=torch.float32, device=z.device)
+    arg = torch.empty((n_seg, c), dtype=torch.int32, device=z.device)
+    _lib.launches += 1
+    check(lib.pcfd_segmax_fwd(z.data_ptr(), z.stride(0), ACT_CODES[act], _ptr(slots), n_seg, seg_len, c,
+                              out.data_ptr(), out.stride(0), arg.data_ptr(), _stream()), 'pcfd_segmax_fwd')
+    return out, arg
+
+
+def segmax_bwd(gout: Tensor, ldgout: int, arg: Tensor, z: Tensor, act, n_seg: int, seg_len: int, c: int) -> Tensor:
+    lib = _lib.load()
+    gz = torch.empty((1, n_seg * seg_len, z.stride(0)), dtype=torch.float32, device=z.device)
+    _lib.launches += 1
+    check(lib.pcfd_segmax_bwd(gout.data_ptr(), ldgout, arg.data_ptr(), z.data_ptr(), z.stride(0), ACT_CODES[act],
+                              n_seg, seg_len, c, gz.data_ptr(), gz.stride(1), _stream()), 'pcfd_segmax_bwd')
+    return gz
+
+
+def fps(pos: Tensor, ratio: float) -> Tensor:
+    """pos (B, n, D) -> int64 (B, m) indices into the flattened (B*n) point array, m = ceil(ratio*n)."""
+    lib = _lib.load()
+    pos = _f32(pos, 'pos').contiguous()
+    b, n, d = pos.shape
+    m = int(math.ceil(ratio * n))
+    idx = torch.empty((b, m), dtype=torch.int64, device=pos.device)
+    _lib.launches += 1
+    check(lib.pcfd_fps(pos.data_ptr(), b, n, d, m, idx.data_ptr(), _stream()), 'pcfd_fps')
+    return idx
+
+
+def ball_query(pos: Tensor, centroid_idx: Tensor, r: float, k: int):
+    """-> (nbr int32 (B*m, k) flattened point indices or -1, count int32 (B*m,))"""
+    lib = _lib.load()
+    b, n, d = pos.shape
+    m = centroid_idx.shape[1]
+    nbr = torch.empty((b * m, k), dtype=torch.int32, device=pos.device)
+    count = torch.empty((b * m,), dtype=torch.int32, device=pos.device)
+    _lib.launches += 1
+    check(lib.pcfd_ball_query(pos.data_ptr(), centroid_idx.data_ptr(), b, n, d, m, float(r), k, nbr.data_ptr(),
+                              count.data_ptr(), _stream()), 'pcfd_ball_query')
+    return nbr, count
+
+
+def sa_edges(nbr: Tensor, n_points_total: int) -> Tensor:
+    lib = _lib.load()
+    m_total, k = nbr.shape
+    slots = torch.empty((m_total, k + 1), dtype=torch.int32, device=nbr.device)
+    _lib.launches += 1
+    check(lib.pcfd_sa_edges(nbr.data_ptr(), m_total, k, n_points_total, slots.data_ptr(), _stream()), 'pcfd_sa_edges')
+    return slots
+
+
+def sa_gather(x: Optional[Tensor], ldx: int, f_in: int, pos: Tensor, centroid_idx: Tensor, slots: Tensor,
+              r: float) -> Tensor:
+    lib = _lib.load()
+    m_total, kp = slots.shape
+    dims = pos.shape[-1]
+    width = f_in + dims
+    ein = torch.empty((1, m_total * kp, round4(width)), dtype=torch.float32, device=pos.device)
+    _lib.launches += 1
+    check(lib.pcfd_sa_gather(_ptr(x), ldx, f_in, pos.data_ptr(), dims, centroid_idx.data_ptr(), slots.data_ptr(),
+                             m_total, kp, float(r), ein.data_ptr(), ein.stride(1), _stream()), 'pcfd_sa_gather')
+    return ein
+
+
+def sa_scatter_bwd(gein: Tensor, ldgein: int, slots: Tensor, f_in: int, gx: Tensor, ldgx: int) -> None:
+    lib = _lib.load()
+    m_total, kp = slots.shape
+    _lib.launches += 1
+    check(lib.pcfd_sa_scatter_bwd(gein.data_ptr(), ldgein, slots.data_ptr(), m_total, kp, f_in, gx.data_ptr(), ldgx,
+                                  _stream()), 'pcfd_sa_scatter_bwd')
+
+
+def gather_cols(data: Tensor, n_geom: int, n_rows: int, f: int, row_ids: Optional[Tensor], first_row: int, n_sel: int,
+                cols, out: Tensor, ldout: int, out_rows_per_geom: int, out_row_offset: int = 0,
+                out_col_offset: int = 0) -> None:
+    lib = _lib.load()
+    arr = (C.c_int32 * len(cols))(*cols)
+    _lib.launches += 1
+    check(lib.pcfd_gather_cols(data.data_ptr(), n_geom, n_rows, f, _ptr(row_ids), first_row, n_sel, arr, len(cols),
+                               out.data_ptr(), ldout, out_rows_per_geom, out_row_offset, out_col_offset, _stream()),
+          'pcfd_gather_cols')
+
+
+def seed_jet(data: Tensor, row_ids: Optional[Tensor], n_sel: int, coord_cols, cj: int) -> Jet:
+    lib = _lib.load()
+    b, n_rows, f = data.shape
+    dims = len(coord_cols)
+    z = Jet.empty(cj, b * n_sel, dims, data.device)
+    arr = (C.c_int32 * dims)(*coord_cols)
+    _lib.launches += 1
+    check(lib.pcfd_seed_jet(data.data_ptr(), b, n_rows, f, _ptr(row_ids), n_sel, arr, dims, cj, z.t.data_ptr(),
+                            z.plane_stride, z.ld, _stream()), 'pcfd_seed_jet')
+    return z
+
+
+def residual_workspace_bytes(n_geom: int, ni: int, nb: int, no: int) -> int:
+    return int(_lib.load().pcfd_residual_workspace_bytes(n_geom, ni, nb, no))
+
+
+def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_ids: Optional[Tensor],
+                  y_int: Jet, y_bnd: Jet, prm: ResidualParams, workspace: Tensor):
+    """-> (gy_int Jet, gy_bnd Jet, out float32[48])"""
+    lib = _lib.load()
+    b, n_rows, f = data.shape
+    ni, nb = internal_ids.shape[1], boundary_ids.shape[1]
+    no = obs_ids.shape[1] if obs_ids is not None else 0
+    gy_int = Jet(torch.empty_like(y_int.t), y_int.width)
+    gy_bnd = Jet(torch.empty_like(y_bnd.t), y_bnd.width)
+    out = torch.empty(_lib.LOSS_OUT_FLOATS, dtype=torch.float32, device=data.device)
+    _lib.launches += 4
+    check(lib.pcfd_residual_loss(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
+                                 nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
+                                 y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), gy_int.t.data_ptr(), gy_bnd.t.data_ptr(),
+                                 out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                 _stream()), 'pcfd_residual_loss')
+    return gy_int, gy_bnd, out
+
+
+def zero_(t: Tensor) -> None:
+    lib = _lib.load()
+    _lib.launches += 1
+    check(lib.pcfd_zero(t.data_ptr(), t.numel(), _stream()), 'pcfd_zero')
+
+
+def advance_seed(seed_dev: Tensor) -> None:
+    lib = _lib.load()
+    _lib.launches += 1
+    check(lib.pcfd_advance_seed(seed_dev.data_ptr(), _stream()), 'pcfd_advance_seed')
+
+
+def set_gemm_engine(engine: int) -> None:
+    check(_lib.load().pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')

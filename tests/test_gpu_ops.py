@@ -1,0 +1,264 @@
+"""Op-level parity of the CUDA kernels, called through the C ABI, against the oracle (index ops:
+bit-exact) and against an fp64 torch restatement of the same algebra (floating-point ops)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, max_rel, rel_l2
+from oracle import pyg_restate
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # relative, fp32 kernels vs fp64 restatement (north-star tolerance)
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from porous_cfd_b200 import ops as o
+    return o
+
+
+def dev(t):
+    return t.cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# index ops: bit-exact
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c'])
+def test_fps_and_ball_query_match_fixture_bit_exact(ops, tag):
+    z = np.load(f'{GOLDEN}/index_ops.npz')
+    nb, n, d, ratio, r, k = z[f'{tag}/meta']
+    nb, n, d, k = int(nb), int(n), int(d), int(k)
+    pos = torch.from_numpy(z[f'{tag}/pos']).reshape(nb, n, d)
+    idx = ops.fps(dev(pos), float(ratio))
+    assert torch.equal(idx.cpu().flatten(), torch.from_numpy(z[f'{tag}/fps']))
+    nbr, count = ops.ball_query(dev(pos), idx, float(r), k)
+    row, col = torch.from_numpy(z[f'{tag}/row']), torch.from_numpy(z[f'{tag}/col'])
+    nbr = nbr.cpu()
+    got_row, got_slot = torch.nonzero(nbr >= 0, as_tuple=True)
+    assert torch.equal(got_row, row)
+    assert torch.equal(nbr[got_row, got_slot].long(), col)
+    assert torch.equal(count.cpu().long(), torch.bincount(row, minlength=nbr.shape[0]))
+
+
+@pytest.mark.parametrize('shape', [(4, 1000, 3, 0.5), (3, 777, 2, 0.25), (2, 4096, 3, 0.25), (1, 8192, 3, 0.5),
+                                   (5, 33, 3, 0.5), (2, 1, 3, 1.0)])
+def test_fps_bit_exact_against_oracle(ops, shape):
+    nb, n, d, ratio = shape
+    g = torch.Generator().manual_seed(n)
+    pos = torch.rand(nb, n, d, generator=g) * 2 - 1
+    want = pyg_restate.fps(pos.reshape(-1, d), torch.arange(nb).repeat_interleave(n), ratio)
+    got = ops.fps(dev(pos), ratio).cpu().flatten()
+    assert torch.equal(got, want)
+    # properties: m = ceil(ratio n) distinct samples per geometry, first one is point 0
+    m = math.ceil(ratio * n)
+    per = got.reshape(nb, m) - (torch.arange(nb) * n)[:, None]
+    assert all(len(set(r.tolist())) == m for r in per) and bool((per[:, 0] == 0).all())
+
+
+def test_fps_ties_pick_lowest_index(ops):
+    pos = torch.tensor([[[0., 0.], [1., 0.], [1., 0.], [0., 1.], [0., 1.], [0.5, 0.5]]])
+    assert ops.fps(dev(pos), 0.5).cpu().flatten().tolist() == [0, 1, 3]
+
+
+@pytest.mark.parametrize('shape', [(3, 500, 3, 0.5, 0.5, 16), (2, 1000, 2, 0.25, 0.3, 64), (2, 300, 3, 0.5, 3.0, 8)])
+def test_ball_query_and_edges_against_oracle(ops, shape):
+    nb, n, d, ratio, r, k = shape
+    g = torch.Generator().manual_seed(7 * n)
+    pos = torch.rand(nb, n, d, generator=g) * 2 - 1
+    flat = pos.reshape(-1, d)
+    batch = torch.arange(nb).repeat_interleave(n)
+    idx = pyg_restate.fps(flat, batch, ratio)
+    row, col = pyg_restate.radius(flat, flat[idx], r, batch, batch[idx], k)
+    nbr, _ = ops.ball_query(dev(pos), dev(idx.reshape(nb, -1)), r, k)
+    got_row, got_slot = torch.nonzero(nbr.cpu() >= 0, as_tuple=True)
+    assert torch.equal(got_row, row) and torch.equal(nbr.cpu()[got_row, got_slot].long(), col)
+    # PyG self-loop rule on the flattened bipartite graph
+    slots = ops.sa_edges(nbr, nb * n).cpu()
+    keep = col != row
+    loops = torch.arange(idx.numel())
+    src, dst = torch.cat([col[keep], loops]), torch.cat([row[keep], loops])
+    want = sorted(zip(dst.tolist(), src.tolist()))
+    r2, s2 = torch.nonzero(slots >= 0, as_tuple=True)
+    got = sorted(zip(r2.tolist(), slots[r2, s2].tolist()))
+    assert got == want
+
+
+def test_sa_gather_matches_message_inputs(ops):
+    nb, n, d, f = 2, 64, 3, 5
+    g = torch.Generator().manual_seed(0)
+    pos = torch.rand(nb, n, d, generator=g) * 2 - 1
+    x = torch.randn(nb * n, 8, generator=g)
+    idx = ops.fps(dev(pos), 0.5)
+    nbr, _ = ops.ball_query(dev(pos), idx, 0.7, 4)
+    slots = ops.sa_edges(nbr, nb * n)
+    ein = ops.sa_gather(dev(x), 8, f, dev(pos), idx, slots, 0.7).cpu()[0]
+    s, flat, ci = slots.cpu().long(), pos.reshape(-1, d), idx.cpu().flatten()
+    for e in range(s.numel()):
+        i, j = e // s.shape[1], int(s.flatten()[e])
+        if j < 0:
+            assert float(ein[e].abs().max()) == 0.0
+        else:
+            want = torch.cat([x[j, :f], flat[j] - flat[ci[i]] / 0.7])
+            assert torch.equal(ein[e, :f + d], want)
+
+
+# ---------------------------------------------------------------------------------------------
+# segmented max / arg-max
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('act', ['silu', 'tanh', None])
+@pytest.mark.parametrize('shape', [(6, 17, 40), (3, 2500, 100), (1, 1, 7)])
+def test_segmax_forward_backward(ops, act, shape):
+    n_seg, seg_len, c = shape
+    g = torch.Generator().manual_seed(1)
+    z = torch.randn(n_seg * seg_len, c, generator=g) * 2
+    z[3 % (n_seg * seg_len)] = z[0]          # exact ties: lowest slot must win
+    slots = (torch.rand(n_seg, seg_len, generator=g) > 0.2).int() - 1 if seg_len > 1 else None
+    f = {'silu': torch.nn.functional.silu, 'tanh': torch.tanh, None: lambda v: v}[act]
+    zr = z.double().requires_grad_(True)
+    a = f(zr).reshape(n_seg, seg_len, c)
+    if slots is not None:
+        valid = (slots >= 0)[:, :, None]
+        a = torch.where(valid, a, torch.full_like(a, -float('inf')))
+    want, warg = torch.max(a, dim=1)
+    empty = torch.isinf(want)
+    want = torch.where(empty, torch.zeros_like(want), want)
+    zd = dev(z)
+    out, arg = ops.segmax_fwd(zd, act, dev(slots) if slots is not None else None, n_seg, seg_len, c)
+    assert max_rel(out[:, :c], want) < 1e-6 or float((out[:, :c].cpu() - want).abs().max()) < 1e-6
+    assert torch.equal(torch.where(empty, torch.full_like(warg, -1), warg), arg.cpu().long())
+    gout = torch.randn(n_seg, c, generator=g)
+    want.backward(gout.double() * (~empty))
+    gz = ops.segmax_bwd(dev(gout), c, arg, zd, act, n_seg, seg_len, c)[0, :, :c].cpu()
+    assert float((gz.double() - zr.grad).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# jet linear layer: forward, backward-to-input, backward-to-weights
+# ---------------------------------------------------------------------------------------------
+
+def act_jet_ref(act, z, dims, order, s):
+    """fp64 torch restatement of the input transform; differentiable."""
+    if act is None:
+        return z * s
+    z0 = z[0]
+    if act == 'silu':
+        sg = torch.sigmoid(z0)
+        f0, d1 = z0 * sg, sg + z0 * sg * (1 - sg)
+        d2 = sg * (1 - sg) * (2 + z0 * (1 - 2 * sg))
+    else:
+        t = torch.tanh(z0)
+        f0, d1 = t, 1 - t * t
+        d2 = -2 * t * (1 - t * t)
+    # the closed forms above are checked against autograd of the activation itself
+    zz = z0.detach().clone().requires_grad_(True)
+    a0 = torch.nn.functional.silu(zz) if act == 'silu' else torch.tanh(zz)
+    a1 = torch.autograd.grad(a0.sum(), zz, create_graph=True)[0]
+    a2 = torch.autograd.grad(a1.sum(), zz)[0]
+    assert torch.allclose(d1, a1.detach(), atol=1e-10) and torch.allclose(d2, a2, atol=1e-10)
+    planes = [f0 * s]
+    if order >= 1:
+        planes += [d1 * z[1 + k] * s for k in range(dims)]
+    if order == 2:
+        planes += [(d2 * z[1 + k] ** 2 + d1 * z[1 + dims + k]) * s for k in range(dims)]
+    return torch.stack(planes)
+
+
+CASES = [  # cj, dims, order, rows, rows_per_geom, k, n, act, use_escale, use_cvec
+    (1, 0, 0, 300, 100, 10, 64, None, False, False),
+    (1, 0, 0, 257, 0, 69, 96, 'silu', False, False),
+    (4, 3, 1, 200, 50, 64, 384, 'silu', False, True),
+    (3, 2, 1, 130, 65, 176, 352, 'silu', True, False),
+    (7, 3, 2, 150, 75, 64, 128, 'silu', True, True),
+    (5, 2, 2, 99, 33, 40, 3, 'tanh', True, False),
+    (7, 3, 2, 64, 64, 3, 64, None, False, False),
+    (4, 3, 1, 1000, 500, 384, 128, 'tanh', False, False),
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_jet_linear_forward_backward(ops, case):
+    cj, dims, order, rows, rpg, k, n, act, use_e, use_c = case
+    g = torch.Generator().manual_seed(rows + k)
+    n_geom = rows // rpg if rpg else 1
+    zin = torch.randn(cj, rows, k, generator=g)
+    w_full = torch.randn(n, k + 5, generator=g) / math.sqrt(k)     # the layer uses columns [2, 2+k) of a wider weight
+    bias = torch.randn(n, generator=g)
+    escale = torch.randn(n_geom, k, generator=g) if use_e else None
+    cvec = torch.randn(n_geom, n, generator=g) if use_c else None
+    gout = torch.randn(cj, rows, n, generator=g)
+
+    # fp64 reference with autograd
+    zr = zin.double().requires_grad_(True)
+    wr = w_full.double().requires_grad_(True)
+    br = bias.double().requires_grad_(True)
+    er = escale.double().requires_grad_(True) if use_e else None
+    cr = cvec.double().requires_grad_(True) if use_c else None
+    geom = (torch.arange(rows) // rpg) if rpg else torch.zeros(rows, dtype=torch.long)
+    s = er[geom] if use_e else torch.ones(rows, k, dtype=torch.float64)
+    a = act_jet_ref(act, zr, dims, order, s)
+    zo = a @ wr[:, 2:2 + k].t()
+    add0 = cr[geom] if use_c else br[None, :]      # with cvec the caller folds the bias into it
+    zo = torch.cat([(zo[0] + add0)[None], zo[1:]])
+    (zo * gout.double()).sum().backward()
+
+    from porous_cfd_b200.ops import Jet
+    zj = Jet.empty(cj, rows, k, 'cuda'); zj.t[:, :, :k].copy_(zin)
+    wd = dev(w_full)
+    ed = dev(escale) if use_e else None      # must outlive tin (tin holds a raw device pointer)
+    tin = ops.make_intrans(act, 0, ed) if (act or use_e) else None
+    cv = dev(cvec) if use_c else None
+    out = ops.jet_linear_fwd(zj, tin, wd, 2, k, None if use_c else dev(bias), cv, rpg, n)
+    assert rel_l2(out.t[:, :, :n].cpu().double(), zo.detach()) < 2e-6
+
+    gj = Jet.empty(cj, rows, n, 'cuda'); gj.t[:, :, :n].copy_(gout)
+    ge = torch.zeros(n_geom, k, device='cuda') if use_e else None
+    gzin = ops.jet_linear_bwd_dx(gj, wd, 2, zj, tin, ge, rpg, k, n)
+    assert rel_l2(gzin.t[:, :, :k].cpu().double(), zr.grad) < 1e-5
+    if use_e:
+        assert rel_l2(ge.cpu().double(), er.grad) < 1e-5
+
+    gw = torch.zeros_like(wd)
+    gb = torch.zeros(n, device='cuda')
+    gc = torch.zeros(n_geom, n, device='cuda') if use_c else None
+    ws = torch.empty(ops.dw_workspace_bytes(cj, rows, rpg, k, n), dtype=torch.uint8, device='cuda')
+    ops.jet_linear_bwd_dw(gj, zj, tin, gw, 2, None if use_c else gb, gc, rpg, k, n, ws)
+    assert rel_l2(gw.cpu().double(), wr.grad) < 1e-5
+    assert float(gw[:, :2].abs().max()) == 0.0 and float(gw[:, 2 + k:].abs().max()) == 0.0   # neighbours untouched
+    if use_c:
+        assert rel_l2(gc.cpu().double(), cr.grad) < 1e-5
+    else:
+        assert rel_l2(gb.cpu().double(), br.grad) < 1e-5
+    # accumulation semantics: a second call doubles the result
+    ops.jet_linear_bwd_dw(gj, zj, tin, gw, 2, None if use_c else gb, gc, rpg, k, n, ws)
+    assert rel_l2(gw.cpu().double(), 2 * wr.grad) < 1e-5
+
+
+def test_dropout_mask_is_consistent_between_passes(ops):
+    """The same (seed, salt) must give the same mask in forward, dX and dW; keep-rate ~ 1-p."""
+    from porous_cfd_b200.ops import Jet
+    cj, rows, k, n, p = 4, 512, 64, 32, 0.25
+    g = torch.Generator().manual_seed(0)
+    zj = Jet.empty(cj, rows, k, 'cuda'); zj.t.copy_(torch.randn(cj, rows, k, generator=g))
+    w = torch.eye(k, device='cuda')[:n].contiguous()                 # zout = first n transformed inputs
+    seed = torch.tensor([1234], dtype=torch.int64, device='cuda')
+    tin = ops.make_intrans(None, 0, None, p, seed, salt=3)
+    out = ops.jet_linear_fwd(zj, tin, w, 0, k, None, None, 0, n).t[:, :, :n]
+    ratio = out / zj.t[:, :, :n]
+    kept = ratio[0] != 0
+    assert abs(float(kept.float().mean()) - (1 - p)) < 0.03
+    assert torch.allclose(ratio[0][kept], torch.full_like(ratio[0][kept], 1 / (1 - p)), rtol=1e-6)
+    for c in range(1, cj):
+        assert torch.equal(ratio[c] != 0, kept)                      # one mask for all jet channels
+    gj = Jet(torch.ones(cj, rows, n, device='cuda'), n)
+    gz = ops.jet_linear_bwd_dx(gj, w, 0, zj, tin, None, 0, k, n).t[:, :, :n]
+    assert torch.equal(gz[0] != 0, kept)
+    # another step seed gives another mask
+    ops.advance_seed(seed)
+    out2 = ops.jet_linear_fwd(zj, tin, w, 0, k, None, None, 0, n).t[0, :, :n]
+    assert not torch.equal(out2 != 0, kept)

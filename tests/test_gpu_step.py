@@ -1,0 +1,178 @@
+"""End-to-end parity of the fused CUDA training step (through the model API and the C ABI) against
+(a) the outputs the UNMODIFIED reference produced (tests/golden fixtures) and (b) the oracle run on
+the host CPU at the layer shapes of the BASELINE configs."""
+import pytest
+import torch
+
+from helpers import TINY, TINY_SHAPE, flat, load_fixture, max_rel, rel_l2
+from oracle import pinn_oracle
+from porous_cfd_b200 import factory, synthetic
+from porous_cfd_b200.dataset.foam_data import FoamData
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # relative tolerance on every loss term and on ||grad - grad_ref|| / ||grad_ref|| (fp32, north star)
+PER_POINT = ['tiny_pipn_pp', 'tiny_pigano', 'tiny_pigano_pp', 'tiny_manufactured_pp']   # no max-pool coupling
+COUPLED = ['tiny_pipn', 'tiny_manufactured']
+
+
+def cuda_model(spec, params):
+    model = factory.build_model(spec)
+    model.load_state_dict(params, strict=True)
+    return model.to('cuda').eval()
+
+
+def run_step(model, data, labels, domain, mode):
+    batch = FoamData(data, labels, domain).to('cuda')
+    res = model.fused_step(batch, laplacian=mode)
+    torch.cuda.synchronize()
+    grads = {k: model.executor.ctx.grads[id(p)].clone() for k, p in model.named_parameters()}
+    return res, grads
+
+
+@pytest.mark.parametrize('name', PER_POINT)
+@pytest.mark.parametrize('mode', ['reference', 'true'])
+def test_step_matches_reference_fixture(name, mode):
+    spec = synthetic.model_spec(name)
+    data, domain, params, out = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    res, grads = run_step(model, data, labels, domain, mode)
+    ref = out[mode]
+    assert res.n_terms == ref['losses'].numel()
+    assert max_rel(res.losses, ref['losses']) < TOL
+    assert abs(float(res.loss) - float(ref['loss'])) / abs(float(ref['loss'])) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(ref['grads'], keys)) < TOL
+    for k in keys:   # every parameter tensor individually (catches a wrong small gradient hidden by a large one)
+        g, r = grads[k].double().cpu(), ref['grads'][k].double()
+        assert float((g - r).norm()) <= TOL * float(r.norm()) + 1e-7 * float(flat(ref['grads'], keys).norm()), k
+    d = spec['dims']
+    assert max_rel(res.out[33:33 + d], ref['u_error']) < TOL and max_rel(res.out[36], ref['p_error']) < TOL
+
+
+@pytest.mark.parametrize('name', COUPLED)
+def test_vanilla_pipn_values_match_and_coupling_gap_is_known(name):
+    """Vanilla PIPN: predictions, boundary/observation losses (value path) match the reference; the
+    Jacobian-dependent terms differ by the max-pool cross-point coupling that the forward-mode jet
+    does not carry yet ('next' row 1)."""
+    spec = synthetic.model_spec(name)
+    data, domain, params, out = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    res, _ = run_step(model, data, labels, domain, 'reference')
+    d = spec['dims']
+    ref = out['reference']['losses']
+    assert max_rel(res.losses[1 + d:2 + 2 * d], ref[1 + d:2 + 2 * d]) < TOL       # boundary terms
+    if spec['enable_data_loss']:
+        assert max_rel(res.losses[2 + 2 * d:], ref[2 + 2 * d:]) < TOL             # observation terms
+    # forward values against the oracle
+    batch = FoamData(data, labels, domain).to('cuda')
+    pts = torch.cat([batch['internal']['C'], batch['boundary']['C']], dim=1)
+    y = model.forward(pts, batch).data.cpu()
+    y_ref = pinn_oracle.forward(spec, params, pts.cpu(), data, labels, domain)
+    assert rel_l2(y.double(), y_ref.double()) < 1e-5
+
+
+@pytest.mark.parametrize('name', PER_POINT)
+def test_training_step_autograd_api(name):
+    """Drop-in seam: loss = model.training_step(batch, i); loss.backward() fills param.grad."""
+    spec = synthetic.model_spec(name)
+    data, domain, params, out = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    batch = FoamData(data, labels, domain).to('cuda')
+    loss = model.training_step(batch, 0)
+    assert loss.requires_grad and loss.dim() == 0
+    (2.0 * loss).backward()
+    ref = out['reference']
+    keys = list(params)
+    got = {k: p.grad for k, p in model.named_parameters()}
+    assert rel_l2(flat(got, keys), 2.0 * flat(ref['grads'], keys)) < TOL
+    assert abs(float(loss) - float(ref['loss'])) / abs(float(ref['loss'])) < TOL
+    assert abs(float(model.logged['Total loss']) - float(ref['loss'])) / abs(float(ref['loss'])) < TOL
+
+
+@pytest.mark.parametrize('name', PER_POINT)
+def test_forward_matches_oracle(name):
+    spec = synthetic.model_spec(name)
+    data, domain, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    batch = FoamData(data, labels, domain).to('cuda')
+    y = model.forward(batch['C'], batch)
+    assert isinstance(y, FoamData) and y.data.shape == (data.shape[0], data.shape[1], spec['dims'] + 1)
+    y_ref = pinn_oracle.forward(spec, params, pinn_oracle.field(data, labels, 'C'), data, labels, domain)
+    assert rel_l2(y.data.cpu().double(), y_ref.double()) < 1e-5
+    # jets() exposes what get_jacobian / get_laplacian / calculate_gradients return in the reference
+    jets = model.jets(batch, 'true')
+    orc = pinn_oracle.training_step(spec, params, data, labels, domain, 'true')
+    assert rel_l2(jets['jacobian'].cpu().double(), orc['jac'].detach().double()) < TOL
+    assert rel_l2(jets['laplacian'].cpu().double(), orc['lap'].detach().double()) < TOL
+    assert rel_l2(jets['d_p'].cpu().double(), orc['dp'].detach().double()) < TOL
+
+
+FULL = [  # spec name, B, NI, NB, NO, nu override (a larger viscosity makes the Hessian path matter)
+    ('abc_pipn_pp', 2, 300, 200, 100, 0.05),
+    ('duct_pigano', 2, 300, 200, 100, 0.05),
+    ('windbreaks_pigano_pp', 2, 256, 192, 64, 0.05),
+    ('manufactured_pipn_pp', 2, 256, 64, 0, 0.01),
+]
+
+
+@pytest.mark.parametrize('case', FULL)
+@pytest.mark.parametrize('mode', ['reference', 'true'])
+def test_full_width_models_match_oracle(case, mode):
+    """Layer shapes of the BASELINE configs (examples/*/train.py), reduced point counts so the CPU
+    oracle (D + D*D + 1 reverse sweeps + double backward) finishes in seconds."""
+    name, b, ni, nb, no, nu = case
+    spec = synthetic.model_spec(name)
+    spec['nu'] = nu
+    torch.manual_seed(3)
+    model = factory.build_model(spec)
+    params = synthetic.rescale_weights({k: v.detach().clone() for k, v in model.state_dict().items()}, 2.0)
+    model.load_state_dict(params)
+    model = model.to('cuda').eval()
+    data, labels, domain = synthetic.make_batch(spec['layout'], b, ni, nb, no, seed=17)
+    orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, mode)
+    res, grads = run_step(model, data, labels, domain, mode)
+    assert max_rel(res.losses, orc['losses']) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(orc['grads'], keys)) < TOL
+
+
+def test_batch_of_identical_geometries_is_idempotent():
+    """Size-independent property at the full BASELINE shape of config 3 (PI-GANO, B=64, 1500/1000/700):
+    every loss term is a mean over geometries, so a batch made of one geometry repeated gives the loss
+    of that geometry and its gradient (per-point model, no cross-geometry coupling)."""
+    spec = synthetic.model_spec('duct_pigano')
+    torch.manual_seed(3)
+    model = factory.build_model(spec).to('cuda').eval()
+    data, labels, domain = synthetic.make_batch(spec['layout'], 1, 1500, 1000, 700, seed=5)
+    res1, g1 = run_step(model, data, labels, domain, 'reference')
+    l1 = res1.losses.clone()
+    rep = 64
+    data_r = data.repeat(rep, 1, 1)
+    domain_r = {k: v.repeat(rep, 1) for k, v in domain.items()}
+    res2, g2 = run_step(model, data_r, labels, domain_r, 'reference')
+    assert max_rel(res2.losses, l1) < 1e-5
+    keys = [k for k, _ in model.named_parameters()]
+    assert rel_l2(flat(g2, keys), flat(g1, keys)) < 1e-4
+
+
+def test_gradient_is_linear_in_loss_weights():
+    """Doubling every loss weight doubles the gradient (checks the fused residual backward)."""
+    spec = synthetic.model_spec('abc_pipn_pp')
+    data, labels, domain = synthetic.make_batch(spec['layout'], 4, 1500, 1000, 700, seed=9)
+    torch.manual_seed(3)
+    m1 = factory.build_model(spec).to('cuda').eval()
+    spec2 = synthetic.model_spec('abc_pipn_pp')
+    spec2['loss_weights'] = [2 * w for w in spec['loss_weights']]
+    m2 = factory.build_model(spec2)
+    m2.load_state_dict(m1.state_dict())
+    m2 = m2.to('cuda').eval()
+    r1, g1 = run_step(m1, data, labels, domain, 'reference')
+    r2, g2 = run_step(m2, data, labels, domain, 'reference')
+    keys = [k for k, _ in m1.named_parameters()]
+    assert rel_l2(flat(g2, keys), 2 * flat(g1, keys)) < 1e-5
+    assert max_rel(r2.losses, 2 * r1.losses) < 1e-6
