@@ -77,7 +77,15 @@ def mlp(x: Tensor, p: dict, prefix: str, n_layers: int, act, last_activation: bo
     return x
 
 
-def set_abstraction_stack(x: Tensor, pos: Tensor, p: dict, prefix: str, spec: dict, act) -> Tensor:
+def max_over_points(h: Tensor) -> Tensor:
+    """torch.max(h, dim=1, keepdim=True)[0] (models/modules.py:81, :190, :214) with the margin probe."""
+    if pr.MARGINS is not None:
+        nb, n, c = h.shape
+        pr.record_margin(h.reshape(nb * n, c), torch.arange(nb).repeat_interleave(n), nb)
+    return torch.max(h, dim=1, keepdim=True)[0]
+
+
+def set_abstraction_stack(x: Tensor, pos: Tensor, p: dict, prefix: str, spec: dict, act, tap=None) -> Tensor:
     """BatchedDecorator(SetAbstractionSeq) (models/modules.py:94-98, 483-527): flatten the batch,
     run every SetAbstraction (fps -> radius -> PointConvNext, :313-325, message :286-292) and the
     optional GlobalSetAbstraction (:412-423), return (B, n_out, E)."""
@@ -98,6 +106,9 @@ def set_abstraction_stack(x: Tensor, pos: Tensor, p: dict, prefix: str, spec: di
         msg = torch.cat([x[src], pos[src] - pos_c[dst] / r], dim=1)   # operator precedence is the reference's
         msg = mlp(msg, p, f'{prefix}layers.Sa-{i}.conv.local_nn.', len(ch) - 1, act, True, fmt='lins.{}')
         x = pr.segment_max_first(msg, dst, idx.shape[0])
+        if tap is not None:      # test hook: expose the per-level features (and their gradients)
+            x.retain_grad()
+            tap.append(x)
         pos, batch = pos_c, batch[idx]
     if len(channels) > len(radii):
         ch = channels[-1]
@@ -125,7 +136,7 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
         local = mlp(pts, p, 'feature_extract.local_feature.', len(spec['fe_local_layers']) - 1, fe_act)
         g = mlp(torch.cat([local, global_in], dim=-1), p, 'feature_extract.global_feature.',
                 len(spec['fe_global_layers']) - 1, fe_act)
-        g = torch.max(g, dim=1, keepdim=True)[0]
+        g = max_over_points(g)
         seg_in = torch.cat([local, g.repeat(1, n, 1)], dim=-1)
         return mlp(seg_in, p, 'decoder.', len(spec['seg_layers']) - 1, act, False,
                    spec.get('seg_dropout'), training)
@@ -153,7 +164,7 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
         if kind == 'PiGano':
             geom_in = torch.cat([field(data, labels, 'boundaryId'), field(data, labels, 'sdf'), pts.detach()], dim=-1)
             ge = mlp(geom_in, p, 'geometry_encoder.linear.', len(spec['geometry_layers']) - 1, act)
-            ge = torch.max(ge, dim=1, keepdim=True)[0]
+            ge = max_over_points(ge)
         else:
             bnd = rows(data, domain['boundary'])
             bnd_c = field(bnd, labels, 'C').detach()
@@ -165,7 +176,7 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
         local = mlp(pts, p, 'points_encoder.', len(spec['local_layers']) - 1, act)
         h = torch.cat([local, ge.repeat(1, n, 1)], dim=-1)
         pe = mlp(par, p, 'branch.linear.', len(spec['branch_layers']) - 1, act)
-        pe = torch.max(pe, dim=1, keepdim=True)[0]
+        pe = max_over_points(pe)
         for k in range(spec['n_operators']):
             # models/modules.py:239-245: Dropout(act(Linear(h))) * par_embedding
             h = act(F.linear(h, p[f'neural_ops.Operator {k}.linear.0.weight'],

@@ -195,9 +195,36 @@ class PygMLP(nn.Module):
         return x
 
 
+# When set to a list, every max-pool appends the smallest gap between the largest and the second
+# largest candidate it saw.  tests/golden/make_golden.py uses it to reject inputs on which an
+# arg-max is decided by the last bit (SiLU is not monotonic, so two different pre-activations can
+# land within one ulp of each other); on such inputs two correct fp32 implementations may route
+# the gradient to different rows and no tolerance-based comparison is meaningful.
+MARGINS = None
+
+
+def record_margin(values: Tensor, index: Tensor, dim_size: int) -> None:
+    if MARGINS is None or values.shape[0] == 0:
+        return
+    with torch.no_grad():
+        v = values.detach().double()
+        idx2 = index[:, None].expand(-1, v.shape[1])
+        top = torch.full((dim_size, v.shape[1]), -float('inf'), dtype=torch.float64).scatter_reduce(0, idx2, v, 'amax')
+        is_top = v == top[index]
+        second = torch.where(is_top, torch.full_like(v, -float('inf')), v)
+        top2 = torch.full((dim_size, v.shape[1]), -float('inf'), dtype=torch.float64).scatter_reduce(0, idx2, second, 'amax')
+        dup = torch.zeros((dim_size, v.shape[1]), dtype=torch.float64).scatter_reduce(0, idx2, is_top.double(), 'sum')
+        gap = torch.where(dup > 1, torch.zeros_like(top), top - top2)
+        gap = gap / torch.clamp(top.abs(), min=1.0)
+        gap = gap[torch.isfinite(gap)]
+        if gap.numel():
+            MARGINS.append(float(gap.min()))
+
+
 def segment_max_first(src: Tensor, index: Tensor, dim_size: int) -> Tensor:
     """out[i] = max over rows with index == i (0 for empty segments); the gradient goes to the
     FIRST row attaining the maximum (arg-max rule, see module docstring)."""
+    record_margin(src, index, dim_size)
     n_feat = src.shape[1]
     out = src.new_zeros((dim_size, n_feat))
     if src.shape[0] == 0:

@@ -186,6 +186,8 @@ def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg:
             ops.zero_(gprev)
             ops.sa_scatter_bwd(gein.t[0], gein.ld, sv['slots'], sv['f_in'], gprev, sv['ldx'])
             gx, ldgx = gprev, sv['ldx']
+            if 'debug' in saved:
+                saved['debug'][li] = (gprev, gein)
 
 
 # ------------------------------------------------------------------------------------------------

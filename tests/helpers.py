@@ -21,6 +21,7 @@ def load_fixture(name):
                      'u_error': torch.from_numpy(z[f'{mode}/u_error']), 'p_error': torch.from_numpy(z[f'{mode}/p_error']),
                      'grads': {k[len(f'{mode}/grad/'):]: torch.from_numpy(z[k]) for k in z.files
                                if k.startswith(f'{mode}/grad/')}}
+    out['seed'] = int(z['seed'])
     return data, domain, params, out
 
 

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from helpers import TINY, TINY_SHAPE, flat, load_fixture, max_rel, rel_l2
-from oracle import pinn_oracle
+from oracle import pinn_oracle, pyg_restate
 from porous_cfd_b200 import factory, synthetic
 from porous_cfd_b200.dataset.foam_data import FoamData
 
@@ -133,8 +133,14 @@ def test_full_width_models_match_oracle(case, mode):
     params = synthetic.rescale_weights({k: v.detach().clone() for k, v in model.state_dict().items()}, 2.0)
     model.load_state_dict(params)
     model = model.to('cuda').eval()
-    data, labels, domain = synthetic.make_batch(spec['layout'], b, ni, nb, no, seed=17)
-    orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, mode)
+    # skip inputs on which a max-pool arg-max is a last-bit tie (gradient routing would be implementation-defined)
+    for seed in range(17, 40):
+        data, labels, domain = synthetic.make_batch(spec['layout'], b, ni, nb, no, seed=seed)
+        pyg_restate.MARGINS = []
+        orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, mode)
+        margin, pyg_restate.MARGINS = min(pyg_restate.MARGINS), None
+        if margin > 2e-5:
+            break
     res, grads = run_step(model, data, labels, domain, mode)
     assert max_rel(res.losses, orc['losses']) < TOL
     keys = list(params)
