@@ -173,7 +173,8 @@ int pcfd_sa_scatter_bwd(const float* gein, int32_t ldgein, const int32_t* slots,
  * FoamData indexing folded into one gather (dataset/foam_data.py:36-61: label -> column slice,
  * sub-domain -> torch.gather):  out[g*out_rows_per_geom + out_row_offset + i][out_col_offset + c]
  *   = data[g][row_ids[g][i]][cols[c]].   row_ids NULL -> rows first_row .. first_row+n_sel-1.
- * cols_host: up to 32 column indices, read on the host at call time.
+ * cols_host: up to 32 column indices, read on the host at call time; NULL = columns 0..n_cols-1
+ * (any width: a strided 2-D copy).
  */
 int pcfd_gather_cols(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
                      const int64_t* row_ids, int64_t first_row, int64_t n_sel,

@@ -154,7 +154,8 @@ struct ColList { int32_t c[32]; };
 
 __global__ void gather_cols_kernel(const float* __restrict__ data, int64_t n_rows, int f,
                                    const int64_t* __restrict__ row_ids, int64_t first_row, int64_t n_sel,
-                                   ColList cols, int n_cols, int64_t total, float* __restrict__ out, int ldout,
+                                   ColList cols, int identity_cols, int n_cols, int64_t total,
+                                   float* __restrict__ out, int ldout,
                                    int64_t out_rows_per_geom, int64_t out_row_offset, int out_col_offset) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -163,7 +164,7 @@ __global__ void gather_cols_kernel(const float* __restrict__ data, int64_t n_row
   const int64_t i = gi % n_sel, g = gi / n_sel;
   const int64_t src_row = row_ids != nullptr ? row_ids[g * n_sel + i] : first_row + i;
   out[(g * out_rows_per_geom + out_row_offset + i) * ldout + out_col_offset + c] =
-      __ldg(data + (g * n_rows + src_row) * f + cols.c[c]);
+      __ldg(data + (g * n_rows + src_row) * f + (identity_cols ? c : cols.c[c]));
 }
 
 __global__ void seed_jet_kernel(const float* __restrict__ data, int64_t n_rows, int f,
@@ -254,17 +255,20 @@ extern "C" int pcfd_gather_cols(const float* data, int32_t n_geom, int64_t n_row
                                 int64_t first_row, int64_t n_sel, const int32_t* cols_host, int32_t n_cols,
                                 float* out, int32_t ldout, int64_t out_rows_per_geom, int64_t out_row_offset,
                                 int32_t out_col_offset, void* stream) {
-  if (!data || !out || !cols_host || n_cols <= 0 || n_cols > 32 || n_geom <= 0 || n_sel < 0) return PCFD_ERR_ARG;
+  if (!data || !out || n_cols <= 0 || n_cols > f || n_geom <= 0 || n_sel < 0) return PCFD_ERR_ARG;
+  if (cols_host != nullptr && n_cols > 32) return PCFD_ERR_ARG;
   if (n_sel == 0) return PCFD_OK;
   ColList cl;
-  for (int i = 0; i < n_cols; ++i) {
-    if (cols_host[i] < 0 || cols_host[i] >= f) return PCFD_ERR_ARG;
-    cl.c[i] = cols_host[i];
-  }
+  for (int i = 0; i < 32; ++i) cl.c[i] = 0;
+  if (cols_host != nullptr)
+    for (int i = 0; i < n_cols; ++i) {
+      if (cols_host[i] < 0 || cols_host[i] >= f) return PCFD_ERR_ARG;
+      cl.c[i] = cols_host[i];
+    }
   const int64_t total = (int64_t)n_geom * n_sel * n_cols;
   gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      data, n_rows, f, row_ids, first_row, n_sel, cl, n_cols, total, out, ldout, out_rows_per_geom, out_row_offset,
-      out_col_offset);
+      data, n_rows, f, row_ids, first_row, n_sel, cl, cols_host == nullptr ? 1 : 0, n_cols, total, out, ldout,
+      out_rows_per_geom, out_row_offset, out_col_offset);
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
 }

@@ -193,7 +193,8 @@ def gather_cols(data: Tensor, n_geom: int, n_rows: int, f: int, row_ids: Optiona
                 cols, out: Tensor, ldout: int, out_rows_per_geom: int, out_row_offset: int = 0,
                 out_col_offset: int = 0) -> None:
     lib = _lib.load()
-    arr = (C.c_int32 * len(cols))(*cols)
+    cols = list(cols)
+    arr = None if cols == list(range(len(cols))) else (C.c_int32 * len(cols))(*cols)
     _lib.launches += 1
     check(lib.pcfd_gather_cols(data.data_ptr(), n_geom, n_rows, f, _ptr(row_ids), first_row, n_sel, arr, len(cols),
                                out.data_ptr(), ldout, out_rows_per_geom, out_row_offset, out_col_offset, _stream()),
