@@ -1,0 +1,147 @@
+"""Training driver: the reference's `train(args, model, train_data, val_data)` and
+`build_arg_parser()` (reference common/training.py:21-85) without Lightning.
+
+The reference hands the loop to `lightning.Trainer`, which silently becomes DDP when several GPUs
+are visible.  Here the data-parallel shell is explicit: one process per GPU
+(torchrun), every rank runs the fused step on its shard of the geometries, the flat fp32 gradient
+is summed with ONE NCCL all-reduce and divided by the world size (DDP's average), then a fused Adam
+updates the flat parameter buffer.  Losses are means over the local shard, so equal shards give the
+same update as one process on the concatenated batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+from argparse import ArgumentParser, Namespace
+from pathlib import Path
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch.utils.data import DataLoader, Dataset
+
+from ..dataset.foam_data import FoamData
+from ..dataset.foam_dataset import collate_fn
+
+
+def get_log_steps(n_data, batch_size):
+    return (n_data // batch_size) + min(1, n_data % batch_size)
+
+
+def build_arg_parser() -> ArgumentParser:
+    """Same flags and defaults as the reference (common/training.py:21-47)."""
+    p = argparse.ArgumentParser()
+    p.add_argument('--n-internal', type=int, default=1000, help='number of internal points to sample')
+    p.add_argument('--n-boundary', type=int, default=200, help='number of boundary points to sample')
+    p.add_argument('--n-observations', type=int, default=500, help='number of observation points to sample')
+    p.add_argument('--batch-size', type=int, default=13)
+    p.add_argument('--precision', type=str, default='bf16-mixed',
+                   help='accepted for compatibility; the CUDA path computes in fp32 (3xTF32 on tensor cores)')
+    p.add_argument('--epochs', type=int, default=3000)
+    p.add_argument('--logs-dir', type=str, default=os.getcwd())
+    p.add_argument('--train-dir', type=str, default='data/train')
+    p.add_argument('--val-dir', type=str, default='data/val')
+    p.add_argument('--model', type=str, help='model type. The available models depend on the experiment')
+    p.add_argument('--name', type=str, default=None)
+    p.add_argument('--checkpoint', type=str, default=None)
+    p.add_argument('--loss-scaler', type=str, default='fixed')
+    return p
+
+
+class FlatAdamTrainer:
+    """Fused step + gradient all-reduce + fused Adam on flat buffers."""
+
+    def __init__(self, model, process_group=None):
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        ex = model.executor
+        # re-point every parameter into one flat buffer so that Adam is a single fused launch
+        total = ex.flat_grad.numel()
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=ex.device)
+        off = 0
+        for p in ex.params:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            off += n
+        if self.world > 1:   # identical replicas
+            dist.broadcast(self.flat_param, 0, group=self.group)
+        opt_cfg = model.configure_optimizers()[0][0]
+        g = opt_cfg.param_groups[0]
+        self.master = torch.nn.Parameter(self.flat_param)
+        self.master.grad = ex.flat_grad
+        self.optimizer = torch.optim.Adam([self.master], lr=g['lr'], betas=g['betas'], eps=g['eps'], fused=True)
+        gamma = model.configure_optimizers()[1][0]['scheduler'].gamma
+        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, gamma)
+
+    def reduce_gradients(self):
+        if self.world > 1:
+            dist.all_reduce(self.model.executor.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.model.executor.flat_grad.mul_(1.0 / self.world)
+
+    def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
+        res = self.model.fused_step(batch, laplacian)
+        self.reduce_gradients()
+        self.optimizer.step()
+        return res
+
+    def end_epoch(self):
+        self.scheduler.step()
+
+
+def shard_batch(batch: FoamData, rank: int, world: int) -> FoamData:
+    """This rank's equal share of the geometries of a batch."""
+    b = batch.data.shape[0]
+    if b % world != 0:
+        raise ValueError(f'batch of {b} geometries does not split evenly over {world} ranks')
+    per = b // world
+    sl = slice(rank * per, (rank + 1) * per)
+    return FoamData(batch.data[sl].contiguous(), batch.labels, {k: v[sl].contiguous() for k, v in batch.domain.items()})
+
+
+def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
+    """Train `model`; writes model_meta.json and model.ckpt under logs_dir/lightning_logs/<name>
+    like the reference.  Under torchrun every rank takes its share of each batch."""
+    distributed = int(os.environ.get('WORLD_SIZE', '1')) > 1
+    if distributed and not dist.is_initialized():
+        dist.init_process_group('nccl')
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
+    device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(device)
+    torch.manual_seed(8421)
+
+    train_loader = DataLoader(train_data, args.batch_size, True, num_workers=0, collate_fn=collate_fn, pin_memory=True)
+    val_loader = DataLoader(val_data, args.batch_size, False, num_workers=0, collate_fn=collate_fn, pin_memory=True)
+    model = model.to(device).train()
+    trainer = FlatAdamTrainer(model)
+    if args.checkpoint:
+        model.load_state_dict(torch.load(args.checkpoint, map_location=device)['state_dict'])
+
+    log_dir = Path(args.logs_dir) / 'lightning_logs' / (args.name or 'version_0')
+    if rank == 0:
+        log_dir.mkdir(parents=True, exist_ok=True)
+        meta = {'Model type': args.model, 'N internal': args.n_internal, 'N boundary': args.n_boundary,
+                'N observations': args.n_observations, 'Precision': args.precision, 'Batch size': args.batch_size}
+        (log_dir / 'model_meta.json').write_text(json.dumps(meta, indent=4))
+
+    history = []
+    for epoch in range(args.epochs):
+        model.train()
+        for batch in train_loader:
+            batch = shard_batch(batch, rank, world) if world > 1 else batch
+            res = trainer.train_step(model.transfer_batch_to_device(batch, device))
+        trainer.end_epoch()
+        if rank == 0:
+            history.append(float(res.loss))
+        if val_loader is not None and len(val_data) > 0:
+            model.eval()
+            for batch in val_loader:
+                model.validation_step(model.transfer_batch_to_device(batch, device))
+        if rank == 0 and (epoch + 1) % 500 == 0:
+            torch.save({'state_dict': model.state_dict(), 'epoch': epoch}, log_dir / f'checkpoint-{epoch}.ckpt')
+    if rank == 0:
+        torch.save({'state_dict': model.state_dict(), 'epoch': args.epochs}, log_dir / 'model.ckpt')
+    return history

@@ -18,6 +18,47 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class KernelProfile:
+    """Optional per-kernel-family timing with CUDA events on the launching stream (bench.py's
+    roofline leg).  `work` is the algorithmic FLOP (GEMM families) or byte count of the launch."""
+
+    def __init__(self):
+        self.records = []   # (name, start_event, end_event, work)
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, work in self.records:
+            d = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'work': 0.0})
+            d['launches'] += 1
+            d['ms'] += a.elapsed_time(b)
+            d['work'] += work
+        return out
+
+
+PROFILE: Optional[KernelProfile] = None
+
+
+class _timed:
+    __slots__ = ('name', 'work', 'a')
+
+    def __init__(self, name: str, work: float = 0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROFILE.records.append((self.name, self.a, b, self.work))
+        return False
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -74,7 +115,8 @@ def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: 
     if out is None:
         out = Jet.empty(zin.cj, zin.rows, n, zin.t.device)
     _lib.launches += 1
-    check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
+    with _timed(f'jet_fwd_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+      check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                   w.data_ptr() + 4 * col_lo, w.stride(0), _ptr(bias), _ptr(cvec),
                                   cvec.stride(0) if cvec is not None else 0,
                                   out.t.data_ptr(), out.plane_stride, out.ld, zin.cj, zin.rows, rows_per_geom, k, n,
@@ -87,7 +129,8 @@ def jet_linear_bwd_dx(gzout: Jet, w: Tensor, col_lo: int, zin: Jet, tin: Optiona
     lib = _lib.load()
     gzin = Jet.empty(zin.cj, zin.rows, k, zin.t.device)
     _lib.launches += 1
-    check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, w.data_ptr() + 4 * col_lo,
+    with _timed(f'jet_dx_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+      check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, w.data_ptr() + 4 * col_lo,
                                      w.stride(0), zin.t.data_ptr(), zin.plane_stride, zin.ld,
                                      C.byref(tin) if tin is not None else None,
                                      gzin.t.data_ptr(), gzin.plane_stride, gzin.ld, _ptr(gescale),
@@ -105,7 +148,8 @@ def jet_linear_bwd_dw(gzout: Jet, zin: Jet, tin: Optional[InTrans], gw: Optional
                       workspace: Tensor) -> None:
     lib = _lib.load()
     _lib.launches += 2 + (2 if (gbias is not None or gcvec is not None) else 0)
-    check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
+    with _timed(f'jet_dw_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+      check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
                                      zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                      (gw.data_ptr() + 4 * col_lo) if gw is not None else None,
                                      gw.stride(0) if gw is not None else 0, _ptr(gbias), _ptr(gcvec),
@@ -120,7 +164,8 @@ def segmax_fwd(z: Tensor, act, slots: Optional[Tensor], n_seg: int, seg_len: int
     out = torch.empty((n_seg, round4(c)), dtype=torch.float32, device=z.device)
     arg = torch.empty((n_seg, c), dtype=torch.int32, device=z.device)
     _lib.launches += 1
-    check(lib.pcfd_segmax_fwd(z.data_ptr(), z.stride(0), ACT_CODES[act], _ptr(slots), n_seg, seg_len, c,
+    with _timed('segmax_fwd', 4.0 * n_seg * seg_len * c):
+      check(lib.pcfd_segmax_fwd(z.data_ptr(), z.stride(0), ACT_CODES[act], _ptr(slots), n_seg, seg_len, c,
                               out.data_ptr(), out.stride(0), arg.data_ptr(), _stream()), 'pcfd_segmax_fwd')
     return out, arg
 
@@ -129,7 +174,8 @@ def segmax_bwd(gout: Tensor, ldgout: int, arg: Tensor, z: Tensor, act, n_seg: in
     lib = _lib.load()
     gz = torch.empty((1, n_seg * seg_len, z.stride(0)), dtype=torch.float32, device=z.device)
     _lib.launches += 1
-    check(lib.pcfd_segmax_bwd(gout.data_ptr(), ldgout, arg.data_ptr(), z.data_ptr(), z.stride(0), ACT_CODES[act],
+    with _timed('segmax_bwd', 8.0 * n_seg * seg_len * c):
+      check(lib.pcfd_segmax_bwd(gout.data_ptr(), ldgout, arg.data_ptr(), z.data_ptr(), z.stride(0), ACT_CODES[act],
                               n_seg, seg_len, c, gz.data_ptr(), gz.stride(1), _stream()), 'pcfd_segmax_bwd')
     return gz
 
@@ -142,7 +188,8 @@ def fps(pos: Tensor, ratio: float) -> Tensor:
     m = int(math.ceil(ratio * n))
     idx = torch.empty((b, m), dtype=torch.int64, device=pos.device)
     _lib.launches += 1
-    check(lib.pcfd_fps(pos.data_ptr(), b, n, d, m, idx.data_ptr(), _stream()), 'pcfd_fps')
+    with _timed('fps', 4.0 * b * n * d + 8.0 * b * m):
+      check(lib.pcfd_fps(pos.data_ptr(), b, n, d, m, idx.data_ptr(), _stream()), 'pcfd_fps')
     return idx
 
 
@@ -154,7 +201,8 @@ def ball_query(pos: Tensor, centroid_idx: Tensor, r: float, k: int):
     nbr = torch.empty((b * m, k), dtype=torch.int32, device=pos.device)
     count = torch.empty((b * m,), dtype=torch.int32, device=pos.device)
     _lib.launches += 1
-    check(lib.pcfd_ball_query(pos.data_ptr(), centroid_idx.data_ptr(), b, n, d, m, float(r), k, nbr.data_ptr(),
+    with _timed('ball_query', 4.0 * b * n * d + 4.0 * b * m * d + 4.0 * b * m * k):
+      check(lib.pcfd_ball_query(pos.data_ptr(), centroid_idx.data_ptr(), b, n, d, m, float(r), k, nbr.data_ptr(),
                               count.data_ptr(), _stream()), 'pcfd_ball_query')
     return nbr, count
 
@@ -176,7 +224,8 @@ def sa_gather(x: Optional[Tensor], ldx: int, f_in: int, pos: Tensor, centroid_id
     width = f_in + dims
     ein = torch.empty((1, m_total * kp, round4(width)), dtype=torch.float32, device=pos.device)
     _lib.launches += 1
-    check(lib.pcfd_sa_gather(_ptr(x), ldx, f_in, pos.data_ptr(), dims, centroid_idx.data_ptr(), slots.data_ptr(),
+    with _timed('sa_gather', 8.0 * m_total * kp * width):
+      check(lib.pcfd_sa_gather(_ptr(x), ldx, f_in, pos.data_ptr(), dims, centroid_idx.data_ptr(), slots.data_ptr(),
                              m_total, kp, float(r), ein.data_ptr(), ein.stride(1), _stream()), 'pcfd_sa_gather')
     return ein
 
@@ -228,7 +277,8 @@ def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_
     gy_bnd = Jet(torch.empty_like(y_bnd.t), y_bnd.width)
     out = torch.empty(_lib.LOSS_OUT_FLOATS, dtype=torch.float32, device=data.device)
     _lib.launches += 4
-    check(lib.pcfd_residual_loss(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
+    with _timed('residual_loss', 8.0 * b * ni * y_int.cj * y_int.ld + 4.0 * b * ni * f + 8.0 * b * nb * y_int.ld):
+      check(lib.pcfd_residual_loss(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
                                  nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
                                  y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), gy_int.t.data_ptr(), gy_bnd.t.data_ptr(),
                                  out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
