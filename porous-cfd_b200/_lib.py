@@ -16,6 +16,7 @@ ACT_CODES = {None: ACT_NONE, 'none': ACT_NONE, 'silu': ACT_SILU, 'tanh': ACT_TAN
 LOSS_KINDS = {'manufactured': 0, 'fixed': 1, 'variable': 2}
 LAP_MODES = {'reference': 0, 'true': 1}
 LOSS_OUT_FLOATS = 48
+DEFAULT_ENGINE = 1   # jet GEMMs: 1 = tcgen05 3xTF32 (tensor cores), 0 = fp32 FFMA (CUDA cores)
 
 ERRORS = {1: 'bad argument (shape / null pointer / unsupported channel count)', 2: 'misaligned pointer',
           3: 'workspace too small', 4: 'device is not sm_100 (no fallback path exists)'}
@@ -95,6 +96,8 @@ def load() -> C.CDLL:
         fn.restype, fn.argtypes = res, args
     if lib.pcfd_abi_version() != 1:
         raise PcfdError('libpcfd_sm100.so ABI version mismatch; rebuild')
+    engine = int(os.environ.get('PCFD_ENGINE', str(DEFAULT_ENGINE)))
+    check(lib.pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')
     _lib = lib
     return lib
 

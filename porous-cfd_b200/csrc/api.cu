@@ -11,7 +11,18 @@ int pcfd_ffma_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, in
 int pcfd_ffma_jet_linear_bwd_dw(const float*, int64_t, int32_t, const float*, int64_t, int32_t, const pcfd_intrans_t*,
                                 float*, int32_t, float*, float*, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
                                 void*, size_t, void*);
+size_t pcfd_ffma_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
+int pcfd_dw_finish(const float*, int, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t, int64_t,
+                   int32_t, int32_t, float*, void*);
 #ifdef PCFD_HAVE_TC
+int pcfd_tc_supported_bwd(int32_t cj, int64_t rows, int32_t k, int32_t n);
+int pcfd_tc_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
+                              const pcfd_intrans_t*, float*, int64_t, int32_t, float*, int32_t, int32_t, int64_t, int64_t,
+                              int32_t, int32_t, void*);
+size_t pcfd_tc_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
+int pcfd_tc_jet_linear_bwd_dw_partials(const float*, int64_t, int32_t, const float*, int64_t, int32_t,
+                                       const pcfd_intrans_t*, int32_t, int64_t, int64_t, int32_t, int32_t, void*, int*,
+                                       void*);
 int pcfd_tc_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
                            int32_t, void*);
@@ -82,6 +93,11 @@ extern "C" int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int3
   if (tin && tin->drop_p > 0.f && !tin->seed_dev) return PCFD_ERR_ARG;
   int rc = ensure_arch();
   if (rc) return rc;
+#ifdef PCFD_HAVE_TC
+  if (g_engine == 1 && pcfd_tc_supported_bwd(cj, rows, k, n))
+    return pcfd_tc_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
+                                     gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);
+#endif
   return pcfd_ffma_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
                                      gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);
 }
@@ -97,6 +113,30 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
   if (tin && tin->drop_p > 0.f && !tin->seed_dev) return PCFD_ERR_ARG;
   int rc = ensure_arch();
   if (rc) return rc;
+  if (workspace_bytes < pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n)) return PCFD_ERR_WORKSPACE;
+#ifdef PCFD_HAVE_TC
+  if (g_engine == 1 && gw != nullptr && pcfd_tc_supported_bwd(cj, rows, k, n) && n >= 32) {
+    int splits = 0;
+    rc = pcfd_tc_jet_linear_bwd_dw_partials(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, cj, rows, rows_per_geom, k,
+                                            n, workspace, &splits, stream);
+    if (rc) return rc;
+    float* partial = reinterpret_cast<float*>(workspace);
+    float* tmp = partial + (size_t)splits * n * k;
+    return pcfd_dw_finish(partial, splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows, rows_per_geom, k, n, tmp,
+                          stream);
+  }
+#endif
   return pcfd_ffma_jet_linear_bwd_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, gw, ldgw, gbias, gcvec, ldgcvec,
                                      cj, rows, rows_per_geom, k, n, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t pcfd_jet_linear_bwd_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k,
+                                                         int32_t n) {
+  if (!pcfd::valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0) return 0;
+  size_t need = pcfd_ffma_dw_workspace_bytes(cj, rows, rows_per_geom, k, n);
+#ifdef PCFD_HAVE_TC
+  const size_t t = pcfd_tc_dw_workspace_bytes(cj, rows, rows_per_geom, k, n);
+  if (t > need) need = t;
+#endif
+  return need;
 }

@@ -520,8 +520,31 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps,
   return PCFD_ERR_ARG;
 }
 
-extern "C" size_t pcfd_jet_linear_bwd_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k,
-                                                         int32_t n) {
+// Shared tail of both engines' dW: fixed-order reduction of the row-split partials into gw (+=), and the
+// per-geometry column sums of the value plane for the bias / per-geometry-constant gradients.
+extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzout, int32_t ldgzout, float* gw,
+                              int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int64_t rows,
+                              int64_t rows_per_geom, int32_t k, int32_t n, float* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gw != nullptr && partial != nullptr) {
+    const int64_t total = (int64_t)n * k;
+    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, n, k, gw, ldgw);
+    PCFD_CHECK_LAUNCH();
+  }
+  if (gbias != nullptr || gcvec != nullptr) {
+    if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
+    const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
+    const int64_t chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    dim3 grid((unsigned)chunks, (unsigned)((n + 31) / 32));
+    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, n, tmp);
+    PCFD_CHECK_LAUNCH();
+    colsum_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tmp, chunks, n, gbias, gcvec, ldgcvec);
+    PCFD_CHECK_LAUNCH();
+  }
+  return PCFD_OK;
+}
+
+extern "C" size_t pcfd_ffma_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   if (!valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0) return 0;
   DwPlan p = plan_dw(cj, rows, rows_per_geom, k, n);
   return ((size_t)p.splits * n * k + (size_t)p.chunks * n) * sizeof(float) + 256;
@@ -532,8 +555,7 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps,
                                            int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int32_t cj,
                                            int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
                                            void* workspace, size_t workspace_bytes, void* stream) {
-  if (workspace_bytes < pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n))
-    return PCFD_ERR_WORKSPACE;
+  if (workspace_bytes < pcfd_ffma_dw_workspace_bytes(cj, rows, rows_per_geom, k, n)) return PCFD_ERR_WORKSPACE;
   DwPlan p = plan_dw(cj, rows, rows_per_geom, k, n);
   float* partial = reinterpret_cast<float*>(workspace);
   float* tmp = partial + (size_t)p.splits * n * k;
@@ -551,17 +573,7 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps,
       default: return PCFD_ERR_ARG;
     }
     PCFD_CHECK_LAUNCH();
-    const int64_t total = (int64_t)n * k;
-    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, p.splits, n, k, gw, ldgw);
-    PCFD_CHECK_LAUNCH();
   }
-  if (gbias != nullptr || gcvec != nullptr) {
-    if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
-    dim3 grid((unsigned)p.chunks, (unsigned)((n + 31) / 32));
-    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, p.rows_per_chunk, n, tmp);
-    PCFD_CHECK_LAUNCH();
-    colsum_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tmp, p.chunks, n, gbias, gcvec, ldgcvec);
-    PCFD_CHECK_LAUNCH();
-  }
-  return PCFD_OK;
+  return pcfd_dw_finish(gw != nullptr ? partial : nullptr, p.splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows,
+                        rows_per_geom, k, n, tmp, stream);
 }
