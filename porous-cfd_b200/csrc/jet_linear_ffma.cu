@@ -404,14 +404,20 @@ __global__ void dw_reduce_kernel(const float* __restrict__ partial, int splits, 
   gw[(int64_t)nn * ldgw + kk] += s;
 }
 
-// column sums of plane 0 of gzout per row chunk (a geometry, or 2048 rows): tmp[chunk][n]
+// column sums of plane 0 of gzout: each chunk (a geometry, or 2048 rows) is cut into sub-blocks of
+// CS_ROWS rows so that the grid fills the GPU; tmp[chunk][sub][n], reduced in fixed order below.
+constexpr int CS_ROWS = 128;
+
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ldg, int64_t rows,
-                                                     int64_t rows_per_chunk, int n, float* tmp) {
+                                                     int64_t rows_per_chunk, int subs, int n, float* tmp) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int col = blockIdx.y * 32 + lane;
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_chunk;
-  const int64_t r_end = min(rows, r_begin + rows_per_chunk);
+  const int64_t chunk = blockIdx.x / subs, sub = blockIdx.x % subs;
+  const int64_t c_begin = chunk * rows_per_chunk;
+  const int64_t c_end = min(rows, c_begin + rows_per_chunk);
+  const int64_t r_begin = c_begin + sub * CS_ROWS;
+  const int64_t r_end = min(c_end, r_begin + CS_ROWS);
   float s = 0.0f;
   if (col < n)
     for (int64_t r = r_begin + wy; r < r_end; r += 8) s += __ldg(g + r * ldg + col);
@@ -425,13 +431,14 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
   }
 }
 
-__global__ void colsum_finish_kernel(const float* __restrict__ tmp, int64_t chunks, int n, float* gbias,
+__global__ void colsum_finish_kernel(const float* __restrict__ tmp, int64_t chunks, int subs, int n, float* gbias,
                                      float* gcvec, int ldgcvec) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n) return;
   float s = 0.0f;
   for (int64_t c = 0; c < chunks; ++c) {
-    const float v = tmp[c * n + col];
+    float v = 0.0f;
+    for (int u = 0; u < subs; ++u) v += tmp[(c * subs + u) * n + col];
     s += v;
     if (gcvec != nullptr) gcvec[c * ldgcvec + col] += v;
   }
@@ -535,10 +542,11 @@ extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzo
     if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
     const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
     const int64_t chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
-    dim3 grid((unsigned)chunks, (unsigned)((n + 31) / 32));
-    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, n, tmp);
+    const int subs = (int)((rows_per_chunk + CS_ROWS - 1) / CS_ROWS);
+    dim3 grid((unsigned)(chunks * subs), (unsigned)((n + 31) / 32));
+    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, subs, n, tmp);
     PCFD_CHECK_LAUNCH();
-    colsum_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tmp, chunks, n, gbias, gcvec, ldgcvec);
+    colsum_finish_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(tmp, chunks, subs, n, gbias, gcvec, ldgcvec);
     PCFD_CHECK_LAUNCH();
   }
   return PCFD_OK;
@@ -547,7 +555,7 @@ extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzo
 extern "C" size_t pcfd_ffma_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   if (!valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0) return 0;
   DwPlan p = plan_dw(cj, rows, rows_per_geom, k, n);
-  return ((size_t)p.splits * n * k + (size_t)p.chunks * n) * sizeof(float) + 256;
+  return ((size_t)p.splits * n * k + (size_t)p.chunks * ((p.rows_per_chunk + 127) / 128) * n) * sizeof(float) + 256;
 }
 
 extern "C" int pcfd_ffma_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* zin,

@@ -257,7 +257,7 @@ using namespace pcfd;
 extern "C" int pcfd_tc_supported_fwd(int32_t cj, int64_t rows, int32_t k, int32_t n, int32_t ldzin, int32_t ldw,
                                      int32_t ldzout) {
   (void)ldzin; (void)ldw; (void)ldzout;
-  return valid_cj(cj) && rows >= 512 && k >= 16 && n >= 16;
+  return valid_cj(cj) && rows >= 512 && (int64_t)k * n >= 64;
 }
 
 extern "C" int pcfd_tc_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t ldzin, const pcfd_intrans_t* tin,
@@ -271,11 +271,11 @@ extern "C" int pcfd_tc_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t 
   a.vec_out = al16(zout) && ldzout % 4 == 0 && zout_ps % 4 == 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (cj) {
-    case 1: return n > 128 ? launch_fwd_tc<1, 16, 256>(a, st) : launch_fwd_tc<1, 16, 128>(a, st);
-    case 3: return launch_fwd_tc<3, 16, 128>(a, st);
-    case 4: return launch_fwd_tc<4, 16, 128>(a, st);
-    case 5: return launch_fwd_tc<5, 16, 64>(a, st);
-    case 7: return launch_fwd_tc<7, 8, 64>(a, st);
+    case 1: return n > 128 ? launch_fwd_tc<1, 16, 256>(a, st) : (n > 32 ? launch_fwd_tc<1, 16, 128>(a, st) : launch_fwd_tc<1, 16, 32>(a, st));
+    case 3: return n > 32 ? launch_fwd_tc<3, 16, 128>(a, st) : launch_fwd_tc<3, 16, 32>(a, st);
+    case 4: return n > 32 ? launch_fwd_tc<4, 16, 128>(a, st) : launch_fwd_tc<4, 16, 32>(a, st);
+    case 5: return n > 32 ? launch_fwd_tc<5, 16, 64>(a, st) : launch_fwd_tc<5, 16, 32>(a, st);
+    case 7: return n > 32 ? launch_fwd_tc<7, 8, 64>(a, st) : launch_fwd_tc<7, 8, 32>(a, st);
   }
   return PCFD_ERR_ARG;
 }
@@ -740,13 +740,14 @@ static TcDwPlan plan_dw_tc(int cj, int64_t rows, int64_t rows_per_geom, int k, i
   TcDwPlan p;
   p.br = cj == 1 ? 32 : 8;
   const int max_nt = cj == 7 ? 64 : (cj == 5 ? 128 : 256);
-  p.nt = k <= 64 ? 64 : (k <= 128 ? 128 : 256);
+  p.nt = k <= 32 ? 32 : (k <= 64 ? 64 : (k <= 128 ? 128 : 256));
   if (p.nt > max_nt) p.nt = max_nt;
   p.tiles_n = (n + 127) / 128;
   p.tiles_k = (k + p.nt - 1) / p.nt;
   const int tiles = p.tiles_n * p.tiles_k;
-  int64_t splits = (148 + tiles - 1) / tiles;
-  const int64_t max_splits = (rows + 32 * p.br - 1) / (32 * p.br);
+  int64_t splits = (2 * 148 + tiles - 1) / tiles;
+  const int64_t min_rows = cj == 1 ? 256 : 128;              // at least a few pipeline stages per CTA
+  const int64_t max_splits = (rows + min_rows - 1) / min_rows;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int64_t rps = (rows + splits - 1) / splits;
@@ -779,7 +780,7 @@ static int launch_dw_tc(const TcDwArgs& a, const TcDwPlan& p, cudaStream_t st) {
 using namespace pcfd;
 
 extern "C" int pcfd_tc_supported_bwd(int32_t cj, int64_t rows, int32_t k, int32_t n) {
-  return valid_cj(cj) && rows >= 512 && k >= 16 && n >= 16;
+  return valid_cj(cj) && rows >= 512 && (int64_t)k * n >= 64;
 }
 
 extern "C" int pcfd_tc_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* w,
@@ -795,18 +796,18 @@ extern "C" int pcfd_tc_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, i
   a.vec_out = al16(gzin) && ldgzin % 4 == 0 && gzin_ps % 4 == 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (cj) {
-    case 1: return k > 128 ? launch_dx_tc<1, 16, 256, 16>(a, st) : launch_dx_tc<1, 16, 128, 16>(a, st);
-    case 3: return launch_dx_tc<3, 16, 128, 16>(a, st);
-    case 4: return launch_dx_tc<4, 16, 128, 16>(a, st);
-    case 5: return launch_dx_tc<5, 16, 64, 8>(a, st);
-    case 7: return launch_dx_tc<7, 8, 64, 8>(a, st);
+    case 1: return k > 128 ? launch_dx_tc<1, 16, 256, 16>(a, st) : (k > 32 ? launch_dx_tc<1, 16, 128, 16>(a, st) : launch_dx_tc<1, 16, 32, 16>(a, st));
+    case 3: return k > 32 ? launch_dx_tc<3, 16, 128, 16>(a, st) : launch_dx_tc<3, 16, 32, 16>(a, st);
+    case 4: return k > 32 ? launch_dx_tc<4, 16, 128, 16>(a, st) : launch_dx_tc<4, 16, 32, 16>(a, st);
+    case 5: return k > 32 ? launch_dx_tc<5, 16, 64, 8>(a, st) : launch_dx_tc<5, 16, 32, 8>(a, st);
+    case 7: return k > 32 ? launch_dx_tc<7, 8, 64, 8>(a, st) : launch_dx_tc<7, 8, 32, 8>(a, st);
   }
   return PCFD_ERR_ARG;
 }
 
 extern "C" size_t pcfd_tc_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   TcDwPlan p = plan_dw_tc(cj, rows, rows_per_geom, k, n);
-  return ((size_t)p.splits * n * k + (size_t)p.chunks * n) * sizeof(float) + 256;
+  return ((size_t)p.splits * n * k + (size_t)p.chunks * ((p.rows_per_chunk + 127) / 128) * n) * sizeof(float) + 256;
 }
 
 // writes partial[splits][n][k] at the start of `workspace`; returns the number of splits through *splits_out
@@ -823,6 +824,7 @@ extern "C" int pcfd_tc_jet_linear_bwd_dw_partials(const float* gzout, int64_t gz
   *splits_out = p.splits;
   cudaStream_t st = (cudaStream_t)stream;
 #define PCFD_DW_CASE(CJ_, BR_)                                                 \
+  if (p.nt == 32) return launch_dw_tc<CJ_, BR_, 32>(a, p, st);                 \
   if (p.nt == 64) return launch_dw_tc<CJ_, BR_, 64>(a, p, st);                 \
   if (p.nt == 128) return launch_dw_tc<CJ_, BR_, 128>(a, p, st);               \
   return launch_dw_tc<CJ_, BR_, 256>(a, p, st);
@@ -830,8 +832,8 @@ extern "C" int pcfd_tc_jet_linear_bwd_dw_partials(const float* gzout, int64_t gz
     case 1: PCFD_DW_CASE(1, 32)
     case 3: PCFD_DW_CASE(3, 8)
     case 4: PCFD_DW_CASE(4, 8)
-    case 5: if (p.nt == 64) return launch_dw_tc<5, 8, 64>(a, p, st); return launch_dw_tc<5, 8, 128>(a, p, st);
-    case 7: return launch_dw_tc<7, 8, 64>(a, p, st);
+    case 5: if (p.nt == 32) return launch_dw_tc<5, 8, 32>(a, p, st); if (p.nt == 64) return launch_dw_tc<5, 8, 64>(a, p, st); return launch_dw_tc<5, 8, 128>(a, p, st);
+    case 7: if (p.nt == 32) return launch_dw_tc<7, 8, 32>(a, p, st); return launch_dw_tc<7, 8, 64>(a, p, st);
   }
 #undef PCFD_DW_CASE
   return PCFD_ERR_ARG;

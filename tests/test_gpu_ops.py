@@ -12,6 +12,7 @@ from oracle import pyg_restate
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4  # relative, fp32 kernels vs fp64 restatement (north-star tolerance)
+GEMM_TOL = 3e-5  # per-layer budget inside that gate (3xTF32 tensor-core engine: ~1e-5 on long row reductions)
 
 
 @pytest.fixture(scope='module')
@@ -178,6 +179,11 @@ CASES = [  # cj, dims, order, rows, rows_per_geom, k, n, act, use_escale, use_cv
     (5, 2, 2, 99, 33, 40, 3, 'tanh', True, False),
     (7, 3, 2, 64, 64, 3, 64, None, False, False),
     (4, 3, 1, 1000, 500, 384, 128, 'tanh', False, False),
+    (7, 3, 2, 1536, 768, 64, 384, 'silu', True, True),
+    (5, 2, 2, 2000, 1000, 176, 352, 'silu', True, False),
+    (1, 0, 0, 4100, 0, 131, 128, 'silu', False, False),
+    (4, 3, 1, 3000, 1500, 128, 4, 'silu', False, False),
+    (3, 2, 1, 2048, 1024, 10, 64, None, False, False),
 ]
 
 
@@ -214,29 +220,29 @@ def test_jet_linear_forward_backward(ops, case):
     tin = ops.make_intrans(act, 0, ed) if (act or use_e) else None
     cv = dev(cvec) if use_c else None
     out = ops.jet_linear_fwd(zj, tin, wd, 2, k, None if use_c else dev(bias), cv, rpg, n)
-    assert rel_l2(out.t[:, :, :n].cpu().double(), zo.detach()) < 2e-6
+    assert rel_l2(out.t[:, :, :n].cpu().double(), zo.detach()) < 5e-6
 
     gj = Jet.empty(cj, rows, n, 'cuda'); gj.t[:, :, :n].copy_(gout)
     ge = torch.zeros(n_geom, k, device='cuda') if use_e else None
     gzin = ops.jet_linear_bwd_dx(gj, wd, 2, zj, tin, ge, rpg, k, n)
-    assert rel_l2(gzin.t[:, :, :k].cpu().double(), zr.grad) < 1e-5
+    assert rel_l2(gzin.t[:, :, :k].cpu().double(), zr.grad) < GEMM_TOL
     if use_e:
-        assert rel_l2(ge.cpu().double(), er.grad) < 1e-5
+        assert rel_l2(ge.cpu().double(), er.grad) < GEMM_TOL
 
     gw = torch.zeros_like(wd)
     gb = torch.zeros(n, device='cuda')
     gc = torch.zeros(n_geom, n, device='cuda') if use_c else None
     ws = torch.empty(ops.dw_workspace_bytes(cj, rows, rpg, k, n), dtype=torch.uint8, device='cuda')
     ops.jet_linear_bwd_dw(gj, zj, tin, gw, 2, None if use_c else gb, gc, rpg, k, n, ws)
-    assert rel_l2(gw.cpu().double(), wr.grad) < 1e-5
+    assert rel_l2(gw.cpu().double(), wr.grad) < GEMM_TOL
     assert float(gw[:, :2].abs().max()) == 0.0 and float(gw[:, 2 + k:].abs().max()) == 0.0   # neighbours untouched
     if use_c:
-        assert rel_l2(gc.cpu().double(), cr.grad) < 1e-5
+        assert rel_l2(gc.cpu().double(), cr.grad) < GEMM_TOL
     else:
-        assert rel_l2(gb.cpu().double(), br.grad) < 1e-5
+        assert rel_l2(gb.cpu().double(), br.grad) < GEMM_TOL
     # accumulation semantics: a second call doubles the result
     ops.jet_linear_bwd_dw(gj, zj, tin, gw, 2, None if use_c else gb, gc, rpg, k, n, ws)
-    assert rel_l2(gw.cpu().double(), 2 * wr.grad) < 1e-5
+    assert rel_l2(gw.cpu().double(), 2 * wr.grad) < GEMM_TOL
 
 
 def test_dropout_mask_is_consistent_between_passes(ops):
