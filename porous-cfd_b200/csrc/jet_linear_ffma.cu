@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) jet_fwd_kernel(FwdArgs a) {
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     lrow[i] = row0 + lp + 16 * i;
-    lgeom[i] = a.rows_per_geom > 0 ? lrow[i] / a.rows_per_geom : 0;
+    lgeom[i] = geom_of(lrow[i], a.rows_per_geom);
   }
 
   float ra[PPT][CJ];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) jet_fwd_kernel(FwdArgs a) {
     if (row >= a.rows) continue;
     float cv[4] = {0.f, 0.f, 0.f, 0.f};
     if (a.cvec != nullptr) {
-      const int64_t g = a.rows_per_geom > 0 ? row / a.rows_per_geom : 0;
+      const int64_t g = geom_of(row, a.rows_per_geom);
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (nc + j < a.n) cv[j] = __ldg(a.cvec + g * a.ldcvec + nc + j);
     }
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) jet_dx_kernel(DxArgs a) {
   for (int i = 0; i < PPT; ++i) {
     const int64_t row = row0 + ty * PPT + i;
     if (row >= a.rows) continue;
-    const int64_t geom = a.rows_per_geom > 0 ? row / a.rows_per_geom : 0;
+    const int64_t geom = geom_of(row, a.rows_per_geom);
     if (a.gescale != nullptr && geom != ge_geom) {
       if (ge_geom >= 0) {
 #pragma unroll
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) jet_dw_kernel(DwArgs a) {
 #pragma unroll
         for (int c = 0; c < CJ; ++c) z[c] = ok ? __ldg(a.zin + c * a.zin_ps + row * a.ldzin + col) : 0.0f;
         if (ok && !plain && col < a.tin.act_cols) {
-          const int64_t geom = a.rows_per_geom > 0 ? row / a.rows_per_geom : 0;
+          const int64_t geom = geom_of(row, a.rows_per_geom);
           float m;
           const float s = in_scale(a.tin, seed, row, geom, col, m);
           jet_act_fwd<CJ>(a.tin.act, s, z);

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
   const int n0 = blockIdx.y * NT;
   const int64_t row = row0 + row_l;
   const bool valid = row < a.rows;
-  const int64_t geom = (a.rows_per_geom > 0 && valid) ? row / a.rows_per_geom : 0;
+  const int64_t geom = valid ? geom_of(row, a.rows_per_geom) : 0;
   const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
   const bool plain = (a.tin.act == PCFD_ACT_NONE && a.tin.escale == nullptr && a.tin.drop_p == 0.0f);
 
@@ -71,10 +71,12 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, false);
 
   const int nchunks = (a.k + BK - 1) / BK;
-  float z[CPT][CJ][4];
-  float4 wv[BPT];
+  // two register buffers: the HBM loads of chunk i+2 are issued while chunk i is transformed (two chunks,
+  // ~64 KB per SM, stay in flight -- enough to cover the memory latency at full HBM bandwidth)
+  float zA[CPT][CJ][4], zB[CPT][CJ][4];
+  float4 wA[BPT], wB[BPT];
 
-  auto load_chunk = [&](int i) {
+  auto load_chunk = [&](int i, float (&z)[CPT][CJ][4], float4 (&wv)[BPT]) {
     const int k0 = i * BK;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
     }
   };
 
-  auto stage_chunk = [&](int i, uint8_t* st) {
+  auto stage_chunk = [&](int i, uint8_t* st, float (&z)[CPT][CJ][4], float4 (&wv)[BPT]) {
     const int k0 = i * BK;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
@@ -159,13 +161,12 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
     }
   };
 
-  load_chunk(0);
-  for (int i = 0; i < nchunks; ++i) {
+  auto process = [&](int i, float (&z)[CPT][CJ][4], float4 (&wv)[BPT]) {
     const int s = i & 1;
     uint8_t* st = smem + s * STAGE_BYTES;
     if (i >= 2) bounded_wait(&mma_done[s], ((i >> 1) - 1) & 1);     // MMAs that read this stage are done
-    stage_chunk(i, st);
-    if (i + 1 < nchunks) load_chunk(i + 1);                          // HBM loads in flight across the barrier
+    stage_chunk(i, st, z, wv);
+    if (i + 2 < nchunks) load_chunk(i + 2, z, wv);
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -189,6 +190,12 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
       tc::mma_commit(&mma_done[s]);
       if (i + 1 == nchunks) tc::mma_commit(&acc_done);
     }
+  };
+  load_chunk(0, zA, wA);
+  if (nchunks > 1) load_chunk(1, zB, wB);
+  for (int i = 0; i < nchunks; i += 2) {
+    process(i, zA, wA);
+    if (i + 1 < nchunks) process(i + 1, zB, wB);
   }
 
   bounded_wait(&acc_done, 0);
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) jet_fwd_tc_kernel(TcFwdArgs a) {
   const int q = warp & 3, hcol = warp >> 2;
   const int64_t orow = row0 + 32 * q + lane;
   const bool ovalid = orow < a.rows;
-  const int64_t ogeom = (a.rows_per_geom > 0 && ovalid) ? orow / a.rows_per_geom : 0;
+  const int64_t ogeom = ovalid ? geom_of(orow, a.rows_per_geom) : 0;
 #pragma unroll
   for (int c = 0; c < CJ; ++c) {
 #pragma unroll
@@ -346,10 +353,10 @@ __global__ void __launch_bounds__(256, 1) jet_dx_tc_kernel(TcDxArgs a) {
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, false);
 
   const int nchunks = (a.n + BK - 1) / BK;
-  float g[CPT][CJ][4];
-  float4 wv[BPT];
+  float gA[CPT][CJ][4], gB[CPT][CJ][4];          // two register buffers: loads run two chunks ahead
+  float4 wA[BPT], wB[BPT];
 
-  auto load_chunk = [&](int i) {
+  auto load_chunk = [&](int i, float (&g)[CPT][CJ][4], float4 (&wv)[BPT]) {
     const int nb0 = i * BK;
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(256, 1) jet_dx_tc_kernel(TcDxArgs a) {
       }
     }
   };
-  auto stage_chunk = [&](uint8_t* st) {
+  auto stage_chunk = [&](uint8_t* st, float (&g)[CPT][CJ][4], float4 (&wv)[BPT]) {
 #pragma unroll
     for (int q = 0; q < CPT; ++q) {
       const int j = half * CPT + q;
@@ -411,13 +418,12 @@ __global__ void __launch_bounds__(256, 1) jet_dx_tc_kernel(TcDxArgs a) {
     }
   };
 
-  load_chunk(0);
-  for (int i = 0; i < nchunks; ++i) {
+  auto process = [&](int i, float (&g)[CPT][CJ][4], float4 (&wv)[BPT]) {
     const int s = i & 1;
     uint8_t* st = smem + s * STAGE_BYTES;
     if (i >= 2) bounded_wait(&mma_done[s], ((i >> 1) - 1) & 1);
-    stage_chunk(st);
-    if (i + 1 < nchunks) load_chunk(i + 1);
+    stage_chunk(st, g, wv);
+    if (i + 2 < nchunks) load_chunk(i + 2, g, wv);
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -441,7 +447,14 @@ __global__ void __launch_bounds__(256, 1) jet_dx_tc_kernel(TcDxArgs a) {
       tc::mma_commit(&mma_done[s]);
       if (i + 1 == nchunks) tc::mma_commit(&acc_done);
     }
+  };
+  load_chunk(0, gA, wA);
+  if (nchunks > 1) load_chunk(1, gB, wB);
+  for (int i = 0; i < nchunks; i += 2) {
+    process(i, gA, wA);
+    if (i + 1 < nchunks) process(i + 1, gB, wB);
   }
+
   bounded_wait(&acc_done, 0);
   tc::tc_fence_after();
 
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(256, 1) jet_dx_tc_kernel(TcDxArgs a) {
   const int q = warp & 3, hcol = warp >> 2;
   const int64_t orow = row0 + 32 * q + lane;
   const bool ovalid = orow < a.rows;
-  const int64_t ogeom = (a.rows_per_geom > 0 && ovalid) ? orow / a.rows_per_geom : 0;
+  const int64_t ogeom = ovalid ? geom_of(orow, a.rows_per_geom) : 0;
   const int64_t geom0 = __shfl_sync(0xffffffffu, ogeom, 0);
   const bool uniform = __all_sync(0xffffffffu, (!ovalid) || ogeom == geom0);
 #pragma unroll 1
@@ -599,10 +612,10 @@ __global__ void __launch_bounds__(256, 1) jet_dw_tc_kernel(TcDwArgs a) {
   const uint32_t tmem_base = tmem_base_s;
   constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, false);
 
-  float gv[APT][4];
-  float zv[BPT][CJ][4];        // [item][channel][point within the group of 4]
+  float gvA[APT][4], gvB[APT][4];                  // two register buffers: loads run two stages ahead
+  float zvA[BPT][CJ][4], zvB[BPT][CJ][4];          // [item][channel][point within the group of 4]
 
-  auto load_chunk = [&](int64_t r0) {
+  auto load_chunk = [&](int64_t r0, float (&gv)[APT][4], float (&zv)[BPT][CJ][4]) {
 #pragma unroll
     for (int t = 0; t < APT; ++t) {
       const int idx = tid + t * 256;
@@ -627,7 +640,7 @@ __global__ void __launch_bounds__(256, 1) jet_dw_tc_kernel(TcDwArgs a) {
       }
     }
   };
-  auto stage_chunk = [&](int64_t r0, uint8_t* st) {
+  auto stage_chunk = [&](int64_t r0, uint8_t* st, float (&gv)[APT][4], float (&zv)[BPT][CJ][4]) {
 #pragma unroll
     for (int t = 0; t < APT; ++t) {
       const int idx = tid + t * 256;
@@ -650,7 +663,7 @@ __global__ void __launch_bounds__(256, 1) jet_dw_tc_kernel(TcDwArgs a) {
           for (int e = 0; e < 4; ++e) {
             const int64_t row = r0 + 4 * pj + e;
             if (row < r_end) {
-              const int64_t geom = a.rows_per_geom > 0 ? row / a.rows_per_geom : 0;
+              const int64_t geom = a.tin.escale != nullptr ? geom_of(row, a.rows_per_geom) : 0;
               float zz[CJ];
 #pragma unroll
               for (int c = 0; c < CJ; ++c) zz[c] = zv[t][c][e];
@@ -676,14 +689,13 @@ __global__ void __launch_bounds__(256, 1) jet_dw_tc_kernel(TcDwArgs a) {
   };
 
   const int nsteps = (int)((r_end - r_begin + BR - 1) / BR);
-  if (nsteps > 0) load_chunk(r_begin);
-  for (int i = 0; i < nsteps; ++i) {
+  auto process = [&](int i, float (&gv)[APT][4], float (&zv)[BPT][CJ][4]) {
     const int s = i & 1;
     const int64_t r0 = r_begin + (int64_t)i * BR;
     uint8_t* st = smem + s * STAGE_BYTES;
     if (i >= 2) bounded_wait(&mma_done[s], ((i >> 1) - 1) & 1);
-    stage_chunk(r0, st);
-    if (i + 1 < nsteps) load_chunk(r0 + BR);
+    stage_chunk(r0, st, gv, zv);
+    if (i + 2 < nsteps) load_chunk(r0 + 2 * BR, gv, zv);
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
@@ -703,6 +715,12 @@ __global__ void __launch_bounds__(256, 1) jet_dw_tc_kernel(TcDwArgs a) {
       tc::mma_commit(&mma_done[s]);
       if (i + 1 == nsteps) tc::mma_commit(&acc_done);
     }
+  };
+  if (nsteps > 0) load_chunk(r_begin, gvA, zvA);
+  if (nsteps > 1) load_chunk(r_begin + BR, gvB, zvB);
+  for (int i = 0; i < nsteps; i += 2) {
+    process(i, gvA, zvA);
+    if (i + 1 < nsteps) process(i + 1, gvB, zvB);
   }
   float* dst = a.partial + (int64_t)blockIdx.y * a.n * a.k;
   const int q = warp & 3, hcol = warp >> 2;
