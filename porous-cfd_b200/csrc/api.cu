@@ -27,6 +27,11 @@ int pcfd_tc_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
                            int32_t, void*);
 int pcfd_tc_supported_fwd(int32_t cj, int64_t rows, int32_t k, int32_t n, int32_t ldzin, int32_t ldw, int32_t ldzout);
+int pcfd_ws_supported_fwd(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t, int32_t,
+                          int64_t, int32_t, int32_t);
+int pcfd_ws_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
+                           const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
+                           int32_t, void*);
 #endif
 }
 
@@ -53,7 +58,7 @@ extern "C" int pcfd_device_arch(int* cc_out_host) {
 
 extern "C" int pcfd_set_gemm_engine(int engine) {
 #ifdef PCFD_HAVE_TC
-  if (engine != 0 && engine != 1) return PCFD_ERR_ARG;
+  if (engine < 0 || engine > 2) return PCFD_ERR_ARG;
 #else
   if (engine != 0) return PCFD_ERR_ARG;
 #endif
@@ -74,6 +79,9 @@ extern "C" int pcfd_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t ldz
   int rc = ensure_arch();
   if (rc) return rc;
 #ifdef PCFD_HAVE_TC
+  if (g_engine == 2 && pcfd_ws_supported_fwd(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, cj, rows, k, n))
+    return pcfd_ws_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
+                                  rows_per_geom, k, n, stream);
   if (g_engine == 1 && pcfd_tc_supported_fwd(cj, rows, k, n, ldzin, ldw, ldzout))
     return pcfd_tc_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
                                   rows_per_geom, k, n, stream);

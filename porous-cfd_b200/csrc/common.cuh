@@ -29,11 +29,11 @@ struct ActD { float f0, f1, f2, f3; };
 // sigmoid / tanh on the SFU (ex2.approx + rcp): ~1e-6 relative error for |z| <= 10, two orders of
 // magnitude inside the 1e-4 parity budget, and ~4x fewer instructions than expf + IEEE division --
 // the input transform is on the critical path of the tensor-core kernels' operand staging.
-__device__ __forceinline__ float fast_sigmoid(float z) { return __frcp_rn(1.0f + __expf(-z)); }
+__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 __device__ __forceinline__ float fast_tanh(float z) {
   const float z2 = z * z;
   if (z2 < 0.01f) return z * (1.0f + z2 * (-0.33333333f + z2 * (0.13333333f - z2 * 0.053968254f)));
-  return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * z));
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
 }
 
 template <bool NEED3>
@@ -54,6 +54,31 @@ __device__ __forceinline__ ActD act_derivs(int act, float z) {
     r.f0 = t;
     r.f1 = d;
     r.f2 = -2.0f * t * d;
+    r.f3 = NEED3 ? -2.0f * d * (1.0f - 3.0f * t * t) : 0.0f;
+  } else {
+    r.f0 = z; r.f1 = 1.0f; r.f2 = 0.0f; r.f3 = 0.0f;
+  }
+  return r;
+}
+
+// compile-time activation: the tensor-core engines dispatch once per tile on the (kernel-uniform) activation
+template <int ACT, bool NEED2, bool NEED3>
+__device__ __forceinline__ ActD act_derivs_t(float z) {
+  ActD r;
+  if (ACT == PCFD_ACT_SILU) {
+    const float s = fast_sigmoid(z);
+    const float t = s * (1.0f - s);
+    const float q = 1.0f - 2.0f * s;
+    r.f0 = z * s;
+    r.f1 = s + z * t;
+    r.f2 = NEED2 ? t * (2.0f + z * q) : 0.0f;
+    r.f3 = NEED3 ? t * (q * (3.0f + z * q) - 2.0f * z * t) : 0.0f;
+  } else if (ACT == PCFD_ACT_TANH) {
+    const float t = fast_tanh(z);
+    const float d = 1.0f - t * t;
+    r.f0 = t;
+    r.f1 = d;
+    r.f2 = NEED2 ? -2.0f * t * d : 0.0f;
     r.f3 = NEED3 ? -2.0f * d * (1.0f - 3.0f * t * t) : 0.0f;
   } else {
     r.f0 = z; r.f1 = 1.0f; r.f2 = 0.0f; r.f3 = 0.0f;
@@ -83,14 +108,22 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
   return z ^ (z >> 31);
 }
-// multiplier applied to element (row, col): 0 (dropped) or 1/(1-p)
-__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t salt, int64_t row, int col, float p, float inv_keep) {
-  uint32_t h = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + salt));
-  h = mix32(h ^ (uint32_t)row);
-  h = mix32(h + 0x9e3779b9U * (uint32_t)col + (uint32_t)((uint64_t)row >> 32));
+// multiplier applied to element (row, col): 0 (dropped) or 1/(1-p).  The hash is staged (seed+salt, then
+// row, then column) so that callers can hoist the first two levels out of their column loops.
+__host__ __device__ __forceinline__ uint32_t dropout_seed_hash(uint64_t seed, uint32_t salt) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + salt));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_row_hash(uint32_t hseed, int64_t row) {
+  return mix32(hseed ^ (uint32_t)row);
+}
+__device__ __forceinline__ float dropout_from_row(uint32_t hrow, int64_t row, int col, float p, float inv_keep) {
+  const uint32_t h = mix32(hrow + 0x9e3779b9U * (uint32_t)col + (uint32_t)((uint64_t)row >> 32));
   // uniform in [0,1): keep when u >= p
-  float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+  const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
   return u >= p ? inv_keep : 0.0f;
+}
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t salt, int64_t row, int col, float p, float inv_keep) {
+  return dropout_from_row(dropout_row_hash(dropout_seed_hash(seed, salt), row), row, col, p, inv_keep);
 }
 
 // Device-side view of pcfd_intrans_t (copied by value into kernel parameters).
@@ -153,6 +186,29 @@ __device__ __forceinline__ void jet_act_fwd(int act, float s, float (&z)[CJ]) {
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       float zk = z[1 + k];
+      if (ORDER >= 2) z[1 + D + k] = f2s * zk * zk + f1s * z[1 + D + k];
+      z[1 + k] = f1s * zk;
+    }
+  }
+}
+
+// jet_act_fwd with the activation fixed at compile time
+template <int CJ, int ACT>
+__device__ __forceinline__ void jet_act_fwd_t(float s, float (&z)[CJ]) {
+  constexpr int D = JetShape<CJ>::D;
+  constexpr int ORDER = JetShape<CJ>::ORDER;
+  if (ACT == PCFD_ACT_NONE) {
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) z[c] *= s;
+    return;
+  }
+  const ActD a = act_derivs_t<ACT, (ORDER >= 2), false>(z[0]);
+  z[0] = a.f0 * s;
+  if (ORDER >= 1) {
+    const float f1s = a.f1 * s, f2s = a.f2 * s;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float zk = z[1 + k];
       if (ORDER >= 2) z[1 + D + k] = f2s * zk * zk + f1s * z[1 + D + k];
       z[1 + k] = f1s * zk;
     }

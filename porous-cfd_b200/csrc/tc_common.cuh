@@ -128,6 +128,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 // wait on an mbarrier phase with a bounded spin: a wedged tensor pipe must fail the launch, not hang the GPU
 __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     uint32_t done;
     asm volatile(
