@@ -29,6 +29,11 @@ int pcfd_tc_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*
 int pcfd_tc_supported_fwd(int32_t cj, int64_t rows, int32_t k, int32_t n, int32_t ldzin, int32_t ldw, int32_t ldzout);
 int pcfd_ws_supported_fwd(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t, int32_t,
                           int64_t, int32_t, int32_t);
+int pcfd_ws_supported_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t, const float*,
+                         int64_t, int32_t, int32_t, int64_t, int32_t, int32_t);
+int pcfd_ws_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
+                              const pcfd_intrans_t*, float*, int64_t, int32_t, float*, int32_t, int32_t, int64_t, int64_t,
+                              int32_t, int32_t, void*);
 int pcfd_ws_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
                            int32_t, void*);
@@ -102,6 +107,10 @@ extern "C" int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int3
   int rc = ensure_arch();
   if (rc) return rc;
 #ifdef PCFD_HAVE_TC
+  if (g_engine == 2 && pcfd_ws_supported_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, gzin, gzin_ps, ldgzin, cj,
+                                            rows, k, n))
+    return pcfd_ws_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
+                                     gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);
   if (g_engine == 1 && pcfd_tc_supported_bwd(cj, rows, k, n))
     return pcfd_tc_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
                                      gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);

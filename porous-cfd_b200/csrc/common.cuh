@@ -256,6 +256,45 @@ __device__ __forceinline__ float jet_act_bwd(int act, float s, float m, const fl
   return ge * m;
 }
 
+// jet_act_bwd with the activation fixed at compile time
+template <int CJ, int ACT>
+__device__ __forceinline__ float jet_act_bwd_t(float s, float m, const float (&z)[CJ], float (&g)[CJ]) {
+  constexpr int D = JetShape<CJ>::D;
+  constexpr int ORDER = JetShape<CJ>::ORDER;
+  float ge = 0.0f;
+  if (ACT == PCFD_ACT_NONE) {
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) { ge += g[c] * z[c] * m; g[c] *= s; }
+    return ge;
+  }
+  const ActD a = act_derivs_t<ACT, (ORDER >= 1), (ORDER >= 2)>(z[0]);
+  ge = g[0] * a.f0;
+  float g0 = g[0] * s * a.f1;
+  if (ORDER >= 1) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float zk = z[1 + k];
+      const float gk = g[1 + k];
+      ge += gk * a.f1 * zk;
+      const float gks = gk * s;
+      g0 += gks * a.f2 * zk;
+      float gzk = gks * a.f1;
+      if (ORDER >= 2) {
+        const float zkk = z[1 + D + k];
+        const float gkk = g[1 + D + k];
+        ge += gkk * (a.f2 * zk * zk + a.f1 * zkk);
+        const float gkks = gkk * s;
+        g0 += gkks * (a.f3 * zk * zk + a.f2 * zkk);
+        gzk += gkks * 2.0f * a.f2 * zk;
+        g[1 + D + k] = gkks * a.f1;
+      }
+      g[1 + k] = gzk;
+    }
+  }
+  g[0] = g0;
+  return ge * m;
+}
+
 inline int check_sm100() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return PCFD_ERR_ARCH;

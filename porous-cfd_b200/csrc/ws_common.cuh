@@ -27,6 +27,12 @@
 namespace pcfd {
 namespace ws {
 
+// geometry of the row-tile kernels (forward, dX): a stage holds 16 contraction entries of 8 slabs of 32 rows
+constexpr int BK = 16;                 // contraction entries per stage
+constexpr int SLAB_BYTES = 32 * 64;    // one slab (32 rows) of a stage, 64-byte rows
+constexpr int A_BYTES = 8 * SLAB_BYTES;
+constexpr int STAGES = 4;
+
 // swizzle selector of the MN-major fp32 layout: 32-byte units XORed within a 128-byte row
 // (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA layout type 1, "SWIZZLE_128B_BASE32B")
 constexpr int SW128_ATOM32 = 132;

@@ -27,10 +27,6 @@
 namespace pcfd {
 namespace ws {
 
-constexpr int BK = 16;                 // contraction entries per stage
-constexpr int SLAB_BYTES = 32 * 64;    // one slab (32 rows) of a stage, 64-byte rows
-constexpr int A_BYTES = 8 * SLAB_BYTES;
-constexpr int STAGES = 4;
 constexpr int GROUP = 128;             // threads of one transform group
 constexpr int W_TMA = STAGES * GROUP / 32, W_MMA = W_TMA + 1, W_EPI = W_TMA + 2;
 constexpr int THREADS = (W_EPI + 8) * 32;
