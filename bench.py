@@ -141,7 +141,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--engine', type=int, default=int(os.environ.get('PCFD_ENGINE', '0')), help='0 = fp32 FFMA, 1 = tcgen05')
+    ap.add_argument('--engine', type=int, default=None,
+                    help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 1 = tcgen05 with thread-staged operands, 0 = fp32 FFMA')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--laplacian', default='reference', choices=['reference', 'true'])
@@ -163,8 +164,10 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=device)
     W, K = max(3, args.warmup), max(1, args.steps)
-    if args.engine:
+    if args.engine is not None:
         ops.set_gemm_engine(args.engine)
+    engine = _lib.load().pcfd_get_gemm_engine()
+    engine_name = {0: 'fp32 FFMA', 1: 'tcgen05 3xTF32 (thread-staged operands)', 2: 'TMA + tcgen05 3xTF32, warp-specialised'}[engine]
 
     model, spec = make_model(device)
     trainer = FlatAdamTrainer(model)
@@ -312,7 +315,7 @@ def main():
                 'unit': 'TFLOP/s', 'frac': achieved / peaks['tflops_sustained'], 'traffic': None,
                 'peak_source': peaks['source'] + ', sustained bf16 cuBLAS (kernel timed inside the step)',
                 'launches': top['launches'], 'avg_launch_ms': top['ms'] / top['launches'],
-                'share_of_step': top['ms'] / ms_prof, 'engine': 'tcgen05 3xTF32' if args.engine else 'fp32 FFMA',
+                'share_of_step': top['ms'] / ms_prof, 'engine': engine_name,
                 'all_jet_gemms': {'tflops': all_gemm_flops / (all_gemm_ms / 1e3) / 1e12, 'share_of_step': all_gemm_ms / ms_prof},
                 'families_ms_per_step': {k: round(v['ms'] / prof_steps, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])}}
     hbm = {}

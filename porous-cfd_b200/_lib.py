@@ -16,7 +16,7 @@ ACT_CODES = {None: ACT_NONE, 'none': ACT_NONE, 'silu': ACT_SILU, 'tanh': ACT_TAN
 LOSS_KINDS = {'manufactured': 0, 'fixed': 1, 'variable': 2}
 LAP_MODES = {'reference': 0, 'true': 1}
 LOSS_OUT_FLOATS = 48
-DEFAULT_ENGINE = 1   # jet GEMMs: 1 = tcgen05 3xTF32 (tensor cores), 0 = fp32 FFMA (CUDA cores)
+DEFAULT_ENGINE = 2   # jet GEMMs: 2 = warp-specialised TMA + tcgen05 3xTF32, 1 = tcgen05 3xTF32 (thread-staged operands), 0 = fp32 FFMA (CUDA cores)
 
 ERRORS = {1: 'bad argument (shape / null pointer / unsupported channel count)', 2: 'misaligned pointer',
           3: 'workspace too small', 4: 'device is not sm_100 (no fallback path exists)'}

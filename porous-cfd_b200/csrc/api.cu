@@ -132,7 +132,7 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
   if (rc) return rc;
   if (workspace_bytes < pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n)) return PCFD_ERR_WORKSPACE;
 #ifdef PCFD_HAVE_TC
-  if (g_engine == 1 && gw != nullptr && pcfd_tc_supported_bwd(cj, rows, k, n)) {
+  if (g_engine >= 1 && gw != nullptr && pcfd_tc_supported_bwd(cj, rows, k, n)) {
     int splits = 0;
     rc = pcfd_tc_jet_linear_bwd_dw_partials(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, cj, rows, rows_per_geom, k,
                                             n, workspace, &splits, stream);

@@ -1,0 +1,376 @@
+// Engine 2, backward of a jet layer to its weights: warp-specialised tcgen05 kernel.
+//
+//   partial[split][n][k] = sum over (channel c, row in split)  gzout[c][row][n] * T(zin)[c][row][k]
+//
+// The contraction runs over the ROWS (points x channels), which is the slow index of both operands in
+// memory, so both are MN-major UMMA operands: TMA brings [R rows x 32 columns x CJ channels] boxes in
+// the 32-byte-atom 128B swizzle (ws_common.cuh) and the tensor core transposes them -- neither
+// gzout^T nor T(zin)^T is ever materialised.  A stage holds E = CJ*R contraction entries (all channels
+// of R points, so the activation jet can be applied to the staged tile in place) of
+//   A = gzout   columns [n0, n0 + MT*128)      (MT UMMA M-tiles of 128 layer outputs)
+//   B = T(zin)  columns [k0, k0 + NTL*NT)      (NTL UMMA N-tiles of NT layer inputs)
+// and the MT x NTL accumulator tiles (<= 512 TMEM columns) stay resident for the whole row range of the
+// CTA.  grid = (passes over the (n, k) plane, row splits); the splits' partial products are reduced in a
+// fixed order by pcfd_dw_finish (deterministic), which also forms the bias / per-geometry gradients.
+//
+//   warps 0-15  four groups of 4 warps; group g transforms ring iterations g, g+4, ...: activation jet /
+//               dropout / branch scaling of the zin tile in place (= TF32 "hi" operand, the tensor core
+//               reads the top 19 bits) and the exact remainders lo = x - trunc_tf32(x) of both operands;
+//               after the main loop the same warps drain the accumulators to the partial buffer
+//   warp 16     TMA producer, warp 17 MMA issuer (D += Ahi*Bhi + Alo*Bhi + Ahi*Blo)
+#include "common.cuh"
+#include "ws_common.cuh"
+
+namespace pcfd {
+namespace ws {
+
+constexpr int DW_GROUPS = 4, DW_GROUP = 128;
+constexpr int DW_W_TMA = DW_GROUPS * DW_GROUP / 32, DW_W_MMA = DW_W_TMA + 1;
+constexpr int DW_THREADS = (DW_W_MMA + 1) * 32;
+constexpr int DW_MAX_STAGES = 8;
+constexpr int DW_SMEM_MAX = 232448 - 2048;      // dynamic shared memory we may ask for (227 KB less static + alignment slack)
+
+struct DwArgs {
+  float* partial;
+  int64_t rows, rows_per_geom, rows_per_split;
+  int k, n;
+  InTrans tin;
+  int mt, ntl;                  // accumulator tiles of one pass: mt x 128 outputs, ntl x NT inputs
+  int passes_k;                 // passes along k (pass index = pn * passes_k + pk)
+  int stages;
+  int vec_out;                  // k % 4 == 0: 16-byte stores into the partial buffer
+};
+
+template <int CJ, int R, int NT>
+__global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                              const __grid_constant__ CUtensorMap tmZ, DwArgs a) {
+  constexpr int E = CJ * R;                       // contraction entries per stage
+  constexpr int BLK = E * 128;                    // one 32-column block of a stage
+  static_assert(E % 8 == 0 && R % 4 == 0 && (R & (R - 1)) == 0, "stage must hold whole MMA K steps");
+  static_assert(BLK % 1024 == 0, "blocks must keep the swizzle phase");
+  constexpr int NB = NT / 32;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t raw_full[DW_MAX_STAGES], ops_ready[DW_MAX_STAGES], stage_free[DW_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int STG = a.stages;
+  const int pn = (int)blockIdx.x / a.passes_k, pk = (int)blockIdx.x - pn * a.passes_k;
+  const int n0 = pn * a.mt * 128, k0 = pk * a.ntl * NT;
+  const int ncols = min(a.n - n0, a.mt * 128), kcols = min(a.k - k0, a.ntl * NT);
+  const int ab = (ncols + 31) >> 5, bb = (kcols + 31) >> 5;      // 32-column blocks actually loaded
+  const int AB = a.mt * 4, BB = a.ntl * NB;                        // blocks the stage layout reserves
+  const uint32_t A_LO = (uint32_t)AB * BLK, B_HI = 2u * AB * BLK, B_LO = B_HI + (uint32_t)BB * BLK;
+  const uint32_t STAGE_BYTES = 2u * (AB + BB) * BLK;
+  const int64_t r_begin = (int64_t)blockIdx.y * a.rows_per_split;
+  const int64_t r_end = min(a.rows, r_begin + a.rows_per_split);
+  const int nsteps = (int)((r_end - r_begin + R - 1) / R);
+
+  if (tid == 0) {
+    for (int s = 0; s < STG; ++s) {
+      tc::mbar_init(&raw_full[s], 1);
+      tc::mbar_init(&ops_ready[s], DW_GROUP);
+      tc::mbar_init(&stage_free[s], 1);
+    }
+    tc::mbar_init(&acc_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == DW_W_MMA) tc::tmem_alloc(&tmem_base_s, 512);
+  if (warp == DW_W_TMA && lane == 0) { prefetch_tmap(&tmG); prefetch_tmap(&tmZ); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == DW_W_TMA) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(ab + bb) * BLK;
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % STG;
+        const uint32_t ph = (uint32_t)(it / STG) & 1;
+        tc::bounded_wait(&stage_free[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        const int row = (int)(r_begin + (int64_t)it * R);
+        mbar_expect_tx(&raw_full[s], tx);
+        for (int b = 0; b < ab; ++b) tma_load_3d(st + b * BLK, &tmG, n0 + b * 32, row, 0, &raw_full[s]);
+        for (int b = 0; b < bb; ++b) tma_load_3d(st + B_HI + b * BLK, &tmZ, k0 + b * 32, row, 0, &raw_full[s]);
+      }
+    }
+  } else if (warp == DW_W_MMA) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, true, true);       // both operands MN-major
+      for (int it = 0; it < nsteps; ++it) {
+        const int s = it % STG;
+        const uint32_t ph = (uint32_t)(it / STG) & 1;
+        tc::bounded_wait(&ops_ready[s], ph);
+        tc::tc_fence_after();
+        const uint32_t sb = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < E / 8; ++ks) {
+          for (int mt = 0; mt < a.mt; ++mt) {
+            const uint64_t da_hi = desc_mnmajor(sb + mt * 4 * BLK + ks * 1024, BLK, 512);
+            const uint64_t da_lo = desc_mnmajor(sb + A_LO + mt * 4 * BLK + ks * 1024, BLK, 512);
+            for (int nl = 0; nl < a.ntl; ++nl) {
+              const uint64_t db_hi = desc_mnmajor(sb + B_HI + nl * NB * BLK + ks * 1024, BLK, 512);
+              const uint64_t db_lo = desc_mnmajor(sb + B_LO + nl * NB * BLK + ks * 1024, BLK, 512);
+              const uint32_t d = tmem_base + (uint32_t)(mt * a.ntl + nl) * NT;
+              tc::mma_tf32(d, da_hi, db_hi, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
+              tc::mma_tf32(d, da_lo, db_hi, IDESC, 1u);
+              tc::mma_tf32(d, da_hi, db_lo, IDESC, 1u);
+            }
+          }
+        }
+        tc::mma_commit(&stage_free[s]);
+      }
+      tc::mma_commit(&acc_full);
+    }
+  } else {
+    // ================================ transform ================================
+    const int g = warp >> 2;
+    const int tt = tid - g * DW_GROUP;
+    const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
+    const uint32_t hseed = dropout_seed_hash(seed, a.tin.salt);
+    const bool scaled = a.tin.escale != nullptr || a.tin.drop_p > 0.0f;
+    const bool plain = a.tin.act == PCFD_ACT_NONE && !scaled;
+    const int a_chunks = ab * (BLK / 16);
+    const int b_chunks = bb * (BLK / 16);
+    const int b_items = bb * R * 8;                 // (block, row, 16-byte chunk) positions, all channels each
+    for (int it = g; it < nsteps; it += DW_GROUPS) {
+      const int s = it % STG;
+      const uint32_t ph = (uint32_t)(it / STG) & 1;
+      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      const int64_t row0 = r_begin + (int64_t)it * R;
+      tc::bounded_wait(&raw_full[s], ph);
+      // ---- A: remainder tile of gzout (same swizzled position in the lo tile)
+      for (int i0 = tt; i0 < a_chunks; i0 += 4 * DW_GROUP) {
+        float4 x[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i0 + q * DW_GROUP < a_chunks) x[q] = *reinterpret_cast<const float4*>(st + (size_t)(i0 + q * DW_GROUP) * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i0 + q * DW_GROUP < a_chunks)
+            *reinterpret_cast<float4*>(st + A_LO + (size_t)(i0 + q * DW_GROUP) * 16) =
+                make_float4(x[q].x - trunc_tf32(x[q].x), x[q].y - trunc_tf32(x[q].y), x[q].z - trunc_tf32(x[q].z),
+                            x[q].w - trunc_tf32(x[q].w));
+      }
+      uint8_t* bt = st + B_HI;
+      if (plain) {
+        for (int i0 = tt; i0 < b_chunks; i0 += 4 * DW_GROUP) {
+          float4 x[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i0 + q * DW_GROUP < b_chunks) x[q] = *reinterpret_cast<const float4*>(bt + (size_t)(i0 + q * DW_GROUP) * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i0 + q * DW_GROUP < b_chunks)
+              *reinterpret_cast<float4*>(bt + (B_LO - B_HI) + (size_t)(i0 + q * DW_GROUP) * 16) =
+                  make_float4(x[q].x - trunc_tf32(x[q].x), x[q].y - trunc_tf32(x[q].y), x[q].z - trunc_tf32(x[q].z),
+                              x[q].w - trunc_tf32(x[q].w));
+        }
+      } else {
+        // ---- B: activation jet in place + remainder tile
+        for (int idx = tt; idx < b_items; idx += DW_GROUP) {
+          const int j = idx & 7, r = (idx >> 3) & (R - 1), blk = idx / (8 * R);
+          uint8_t* base = bt + blk * BLK + r * 128 + ((((uint32_t)(j >> 1) ^ (uint32_t)(r & 3)) << 5) | ((uint32_t)(j & 1) << 4));
+          float v[CJ][4];
+#pragma unroll
+          for (int c = 0; c < CJ; ++c) {
+            const float4 x = *reinterpret_cast<const float4*>(base + c * (R * 128));
+            v[c][0] = x.x; v[c][1] = x.y; v[c][2] = x.z; v[c][3] = x.w;
+          }
+          const int64_t row = row0 + r;
+          const int col0 = k0 + blk * 32 + j * 4;
+          if (row < a.rows && col0 < a.tin.act_cols) {
+            const int64_t geom = a.tin.escale != nullptr ? geom_of(row, a.rows_per_geom) : 0;
+            transform_dispatch<CJ>(v, a.tin, scaled, hseed, row, geom, col0, a.tin.act_cols - col0);
+#pragma unroll
+            for (int c = 0; c < CJ; ++c)
+              *reinterpret_cast<float4*>(base + c * (R * 128)) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+          }
+#pragma unroll
+          for (int c = 0; c < CJ; ++c)
+            *reinterpret_cast<float4*>(base + (B_LO - B_HI) + c * (R * 128)) =
+                make_float4(v[c][0] - trunc_tf32(v[c][0]), v[c][1] - trunc_tf32(v[c][1]), v[c][2] - trunc_tf32(v[c][2]),
+                            v[c][3] - trunc_tf32(v[c][3]));
+        }
+      }
+      tc::fence_proxy_async();
+      mbar_arrive(&ops_ready[s]);
+    }
+
+    // ================================ epilogue: accumulators -> partial[split] ================================
+    const int q = warp & 3;                           // TMEM lane quarter this warp may read
+    const int cgrp = warp >> 2;                       // column blocks cgrp, cgrp + 4, ...
+    const int blocks_per_mt = a.ntl * NB;
+    const int total_cb = a.mt * blocks_per_mt;
+    float* dst = a.partial + (int64_t)blockIdx.y * a.n * a.k;
+    if (nsteps > 0) {
+      tc::bounded_wait(&acc_full, 0);
+      tc::tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cbi = cgrp; cbi < total_cb; cbi += DW_GROUPS) {
+      const int mt = cbi / blocks_per_mt;
+      const int kl = (cbi - mt * blocks_per_mt) * 32;
+      const int nn = n0 + mt * 128 + 32 * q + lane;
+      const int kk0 = k0 + kl;
+      if (kl >= kcols || mt * 128 >= ncols) continue;           // warp-uniform
+      uint32_t v[32];
+      if (nsteps > 0) {
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)cbi * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (nn < a.n) {
+        float* p = dst + (int64_t)nn * a.k + kk0;
+        if (a.vec_out && kk0 + 32 <= a.k) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4*>(p + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kk0 + i < a.k) p[i] = __uint_as_float(v[i]);
+        }
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == DW_W_MMA) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host: pass / split plan -------------------------------------------------------------------
+struct DwPlan {
+  int r, e, nt, mt, ntl, passes_n, passes_k, stages, splits;
+  int64_t rows_per_split;
+  int64_t chunks, rows_per_chunk;     // column-sum scratch of pcfd_dw_finish
+};
+
+static inline int dw_rows_per_stage(int cj) { return cj == 1 ? 16 : (cj == 4 ? 4 : 8); }
+
+static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n) {
+  DwPlan p;
+  p.r = dw_rows_per_stage(cj);
+  p.e = cj * p.r;
+  p.nt = k <= 64 ? 64 : 128;
+  const int blk = p.e * 128;
+  const int mt_all = (n + 127) / 128, ntl_all = (k + p.nt - 1) / p.nt;
+  double best = 1e300;
+  p.mt = 1; p.ntl = 1; p.stages = 0;
+  for (int mt = 1; mt <= mt_all && mt <= 4; ++mt) {
+    for (int ntl = 1; ntl <= ntl_all && mt * ntl * p.nt <= 512; ++ntl) {
+      const int stage_bytes = 2 * (mt * 4 + ntl * p.nt / 32) * blk;
+      int stages = DW_SMEM_MAX / stage_bytes;
+      if (stages < 2) continue;
+      if (stages > DW_MAX_STAGES) stages = DW_MAX_STAGES;
+      const int pn = (mt_all + mt - 1) / mt, pk = (ntl_all + ntl - 1) / ntl;
+      // HBM traffic of the operands (each pass along k re-reads gzout, each pass along n re-reads zin);
+      // fewer than 3 stages cannot cover the TMA -> transform -> MMA latency chain
+      double cost = (double)n * pk + (double)k * pn;
+      if (stages < 3) cost *= 1.5;
+      if (cost < best - 1e-9 || (cost < best + 1e-9 && stages > p.stages)) {
+        best = cost; p.mt = mt; p.ntl = ntl; p.stages = stages; p.passes_n = pn; p.passes_k = pk;
+      }
+    }
+  }
+  const int passes = p.passes_n * p.passes_k;
+  int64_t splits = num_sms() / passes;
+  if (splits < 1) splits = 1;
+  const int64_t min_rows = 8 * (int64_t)p.r;                       // a few ring iterations per CTA
+  const int64_t max_splits = (rows + min_rows - 1) / min_rows;
+  if (splits > max_splits) splits = max_splits;
+  int64_t rps = (rows + splits - 1) / splits;
+  rps = (rps + p.r - 1) / p.r * p.r;
+  p.rows_per_split = rps;
+  p.splits = (int)((rows + rps - 1) / rps);
+  p.rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
+  p.chunks = (rows + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  return p;
+}
+
+template <int CJ, int R, int NT>
+static int launch_dw(const float* gzout, int64_t gzout_ps, int ldgzout, const float* zin, int64_t zin_ps, int ldzin,
+                     DwArgs a, const DwPlan& p, cudaStream_t st) {
+  CUtensorMap tmG, tmZ;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.n, (uint64_t)a.rows, (uint64_t)CJ};
+    const uint64_t str[2] = {(uint64_t)ldgzout * 4, (uint64_t)gzout_ps * 4};
+    const uint32_t box[3] = {32, (uint32_t)R, (uint32_t)CJ};
+    if (!make_tmap(&tmG, gzout, 3, dims, str, box, SW128_ATOM32)) return PCFD_ERR_ARG;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.k, (uint64_t)a.rows, (uint64_t)CJ};
+    const uint64_t str[2] = {(uint64_t)ldzin * 4, (uint64_t)zin_ps * 4};
+    const uint32_t box[3] = {32, (uint32_t)R, (uint32_t)CJ};
+    if (!make_tmap(&tmZ, zin, 3, dims, str, box, SW128_ATOM32)) return PCFD_ERR_ARG;
+  }
+  const int stage_bytes = 2 * (p.mt * 4 + p.ntl * NT / 32) * (CJ * R * 128);
+  const int smem = p.stages * stage_bytes + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(ws_dw_kernel<CJ, R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_MAX + 1024);
+    if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+    configured = DW_SMEM_MAX + 1024;
+  }
+  dim3 grid((unsigned)(p.passes_n * p.passes_k), (unsigned)p.splits);
+  ws_dw_kernel<CJ, R, NT><<<grid, DW_THREADS, smem, st>>>(tmG, tmZ, a);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+}  // namespace ws
+}  // namespace pcfd
+
+using namespace pcfd;
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int pcfd_ws_supported_dw(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* zin, int64_t zin_ps,
+                                    int32_t ldzin, int32_t cj, int64_t rows, int32_t k, int32_t n) {
+  if (!valid_cj(cj) || rows < 512 || (int64_t)k * n < 64) return 0;
+  if (rows >= (int64_t)1 << 31) return 0;
+  if (!al16(gzout) || !al16(zin)) return 0;
+  if (ldgzout % 4 || ldzin % 4) return 0;
+  if (cj > 1 && (gzout_ps % 4 || zin_ps % 4)) return 0;
+  return ws::encode_fn() != nullptr;
+}
+
+extern "C" size_t pcfd_ws_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
+  ws::DwPlan p = ws::plan_dw(cj, rows, rows_per_geom, k, n);
+  return ((size_t)p.splits * n * k + (size_t)p.chunks * ((p.rows_per_chunk + 127) / 128) * n) * sizeof(float) + 256;
+}
+
+// writes partial[splits][n][k] at the start of `workspace`; returns the number of splits through *splits_out
+extern "C" int pcfd_ws_jet_linear_bwd_dw_partials(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* zin,
+                                                  int64_t zin_ps, int32_t ldzin, const pcfd_intrans_t* tin, int32_t cj,
+                                                  int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
+                                                  void* workspace, int* splits_out, void* stream) {
+  ws::DwPlan p = ws::plan_dw(cj, rows, rows_per_geom, k, n);
+  if (p.stages < 2) return PCFD_ERR_ARG;
+  if (cj == 1) { gzout_ps = (int64_t)rows * ldgzout; zin_ps = (int64_t)rows * ldzin; }
+  ws::DwArgs a{reinterpret_cast<float*>(workspace), rows, rows_per_geom, p.rows_per_split, k, n, make_intrans(tin, k),
+               p.mt, p.ntl, p.passes_k, p.stages, (k % 4 == 0 && al16(workspace)) ? 1 : 0};
+  *splits_out = p.splits;
+  cudaStream_t st = (cudaStream_t)stream;
+#define PCFD_WS_DW(CJ_, R_)                                                                                    \
+  return p.nt == 64 ? ws::launch_dw<CJ_, R_, 64>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st)       \
+                    : ws::launch_dw<CJ_, R_, 128>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st);
+  switch (cj) {
+    case 1: PCFD_WS_DW(1, 16)
+    case 3: PCFD_WS_DW(3, 8)
+    case 4: PCFD_WS_DW(4, 4)
+    case 5: PCFD_WS_DW(5, 8)
+    case 7: PCFD_WS_DW(7, 8)
+  }
+#undef PCFD_WS_DW
+  return PCFD_ERR_ARG;
+}

@@ -31,43 +31,6 @@ constexpr int GROUP = 128;             // threads of one transform group
 constexpr int W_TMA = STAGES * GROUP / 32, W_MMA = W_TMA + 1, W_EPI = W_TMA + 2;
 constexpr int THREADS = (W_EPI + 8) * 32;
 
-// activation jet of the (up to) 4 columns of one staged 16-byte chunk, all channels
-template <int CJ, int ACT, bool SCALED>
-__device__ __forceinline__ void transform_chunk(float (&v)[CJ][4], const InTrans& tin, uint32_t hseed, int64_t row,
-                                                int64_t geom, int col0, int ncols) {
-  uint32_t hrow = 0;
-  if (SCALED && tin.drop_p > 0.0f) hrow = dropout_row_hash(hseed, row);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (e < ncols) {
-      float sc = 1.0f;
-      if (SCALED) {
-        if (tin.drop_p > 0.0f) sc = dropout_from_row(hrow, row, col0 + e, tin.drop_p, tin.inv_keep);
-        if (tin.escale != nullptr) sc *= __ldg(tin.escale + geom * tin.ldescale + col0 + e);
-      }
-      float zz[CJ];
-#pragma unroll
-      for (int c = 0; c < CJ; ++c) zz[c] = v[c][e];
-      jet_act_fwd_t<CJ, ACT>(sc, zz);
-#pragma unroll
-      for (int c = 0; c < CJ; ++c) v[c][e] = zz[c];
-    }
-  }
-}
-template <int CJ>
-__device__ __forceinline__ void transform_dispatch(float (&v)[CJ][4], const InTrans& tin, bool scaled, uint32_t hseed,
-                                                   int64_t row, int64_t geom, int col0, int ncols) {
-  if (tin.act == PCFD_ACT_SILU) {
-    if (scaled) transform_chunk<CJ, PCFD_ACT_SILU, true>(v, tin, hseed, row, geom, col0, ncols);
-    else transform_chunk<CJ, PCFD_ACT_SILU, false>(v, tin, hseed, row, geom, col0, ncols);
-  } else if (tin.act == PCFD_ACT_TANH) {
-    if (scaled) transform_chunk<CJ, PCFD_ACT_TANH, true>(v, tin, hseed, row, geom, col0, ncols);
-    else transform_chunk<CJ, PCFD_ACT_TANH, false>(v, tin, hseed, row, geom, col0, ncols);
-  } else {
-    transform_chunk<CJ, PCFD_ACT_NONE, true>(v, tin, hseed, row, geom, col0, ncols);
-  }
-}
-
 struct FwdArgs {
   float* zout; int64_t zout_ps; int ldzout;
   const float* bias; const float* cvec; int ldcvec;
