@@ -34,6 +34,11 @@ int pcfd_ws_supported_dx(const float*, int64_t, int32_t, const float*, int32_t, 
 int pcfd_ws_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
                               const pcfd_intrans_t*, float*, int64_t, int32_t, float*, int32_t, int32_t, int64_t, int64_t,
                               int32_t, int32_t, void*);
+int pcfd_ws_supported_dw(const float*, int64_t, int32_t, const float*, int64_t, int32_t, int32_t, int64_t, int32_t, int32_t);
+size_t pcfd_ws_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
+int pcfd_ws_jet_linear_bwd_dw_partials(const float*, int64_t, int32_t, const float*, int64_t, int32_t,
+                                       const pcfd_intrans_t*, int32_t, int64_t, int64_t, int32_t, int32_t, void*, int*,
+                                       void*);
 int pcfd_ws_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
                            int32_t, void*);
@@ -132,6 +137,16 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
   if (rc) return rc;
   if (workspace_bytes < pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n)) return PCFD_ERR_WORKSPACE;
 #ifdef PCFD_HAVE_TC
+  if (g_engine == 2 && gw != nullptr && pcfd_ws_supported_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, cj, rows, k, n)) {
+    int splits = 0;
+    rc = pcfd_ws_jet_linear_bwd_dw_partials(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, cj, rows, rows_per_geom, k,
+                                            n, workspace, &splits, stream);
+    if (rc) return rc;
+    float* partial = reinterpret_cast<float*>(workspace);
+    float* tmp = partial + (size_t)splits * n * k;
+    return pcfd_dw_finish(partial, splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows, rows_per_geom, k, n, tmp,
+                          stream);
+  }
   if (g_engine >= 1 && gw != nullptr && pcfd_tc_supported_bwd(cj, rows, k, n)) {
     int splits = 0;
     rc = pcfd_tc_jet_linear_bwd_dw_partials(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, cj, rows, rows_per_geom, k,
@@ -154,6 +169,8 @@ extern "C" size_t pcfd_jet_linear_bwd_dw_workspace_bytes(int32_t cj, int64_t row
 #ifdef PCFD_HAVE_TC
   const size_t t = pcfd_tc_dw_workspace_bytes(cj, rows, rows_per_geom, k, n);
   if (t > need) need = t;
+  const size_t u = pcfd_ws_dw_workspace_bytes(cj, rows, rows_per_geom, k, n);
+  if (u > need) need = u;
 #endif
   return need;
 }

@@ -180,6 +180,19 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of the (converged) warp.  The producer / MMA-issuer warps run their loops with all 32 lanes so that
+// addresses, descriptors and coordinates stay in uniform registers (UTMALDG / UTCHMMA take uniform operands; code
+// under `if (lane == 0)` makes the compiler wrap every such instruction in an ELECT + R2UR "waterfall" loop, which
+// costs ~150 cycles per MMA -- measured with scripts/probe/mma_rate.cu), and only the issue itself is predicated.
+// elect.sync returns the same leader for the same member mask, so tcgen05.commit sees the MMAs of the same thread.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -18,6 +18,8 @@
 //               reads the top 19 bits) and the exact remainders lo = x - trunc_tf32(x) of both operands;
 //               after the main loop the same warps drain the accumulators to the partial buffer
 //   warp 16     TMA producer, warp 17 MMA issuer (D += Ahi*Bhi + Alo*Bhi + Ahi*Blo)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ws_common.cuh"
 
@@ -37,7 +39,7 @@ struct DwArgs {
   InTrans tin;
   int mt, ntl;                  // accumulator tiles of one pass: mt x 128 outputs, ntl x NT inputs
   int passes_k;                 // passes along k (pass index = pn * passes_k + pk)
-  int stages;
+  int stages, groups;           // ring depth; transform groups in use (groups divides stages, see plan_dw)
   int vec_out;                  // k % 4 == 0: 16-byte stores into the partial buffer
 };
 
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
   __shared__ __align__(8) uint64_t acc_full;
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int STG = a.stages;
   const int pn = (int)blockIdx.x / a.passes_k, pk = (int)blockIdx.x - pn * a.passes_k;
   const int n0 = pn * a.mt * 128, k0 = pk * a.ntl * NT;
@@ -87,37 +89,41 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
 
   if (warp == DW_W_TMA) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)(ab + bb) * BLK;
-      for (int it = 0; it < nsteps; ++it) {
-        const int s = it % STG;
-        const uint32_t ph = (uint32_t)(it / STG) & 1;
-        tc::bounded_wait(&stage_free[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-        const int row = (int)(r_begin + (int64_t)it * R);
+    const uint32_t tx = (uint32_t)(ab + bb) * BLK;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      tc::bounded_wait(&stage_free[s], ph ^ 1);
+      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      const int row = (int)r_begin + it * R;
+      if (elect_one()) {
         mbar_expect_tx(&raw_full[s], tx);
         for (int b = 0; b < ab; ++b) tma_load_3d(st + b * BLK, &tmG, n0 + b * 32, row, 0, &raw_full[s]);
         for (int b = 0; b < bb; ++b) tma_load_3d(st + B_HI + b * BLK, &tmZ, k0 + b * 32, row, 0, &raw_full[s]);
       }
+      __syncwarp();
+      if (++s == STG) { s = 0; ph ^= 1; }
     }
   } else if (warp == DW_W_MMA) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, true, true);       // both operands MN-major
-      for (int it = 0; it < nsteps; ++it) {
-        const int s = it % STG;
-        const uint32_t ph = (uint32_t)(it / STG) & 1;
-        tc::bounded_wait(&ops_ready[s], ph);
-        tc::tc_fence_after();
-        const uint32_t sb = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, true, true);       // both operands MN-major
+    const uint64_t dbase = desc_mnmajor(tc::smem_u32(smem), BLK, 512);        // + (byte offset >> 4) in the address field
+    const uint32_t a_lo = A_LO >> 4, b_hi = B_HI >> 4, b_lo = B_LO >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      tc::bounded_wait(&ops_ready[s], ph);
+      tc::tc_fence_after();
+      const uint64_t ds = dbase + (uint64_t)(((uint32_t)s * STAGE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < E / 8; ++ks) {
           for (int mt = 0; mt < a.mt; ++mt) {
-            const uint64_t da_hi = desc_mnmajor(sb + mt * 4 * BLK + ks * 1024, BLK, 512);
-            const uint64_t da_lo = desc_mnmajor(sb + A_LO + mt * 4 * BLK + ks * 1024, BLK, 512);
+            const uint64_t da_hi = ds + (uint32_t)((mt * 4 * BLK + ks * 1024) >> 4);
+            const uint64_t da_lo = da_hi + a_lo;
             for (int nl = 0; nl < a.ntl; ++nl) {
-              const uint64_t db_hi = desc_mnmajor(sb + B_HI + nl * NB * BLK + ks * 1024, BLK, 512);
-              const uint64_t db_lo = desc_mnmajor(sb + B_LO + nl * NB * BLK + ks * 1024, BLK, 512);
+              const uint64_t db_hi = ds + b_hi + (uint32_t)((nl * NB * BLK + ks * 1024) >> 4);
+              const uint64_t db_lo = db_hi + (b_lo - b_hi);
               const uint32_t d = tmem_base + (uint32_t)(mt * a.ntl + nl) * NT;
               tc::mma_tf32(d, da_hi, db_hi, IDESC, (it > 0 || ks > 0) ? 1u : 0u);
               tc::mma_tf32(d, da_lo, db_hi, IDESC, 1u);
@@ -127,8 +133,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
         }
         tc::mma_commit(&stage_free[s]);
       }
-      tc::mma_commit(&acc_full);
+      __syncwarp();
+      if (++s == STG) { s = 0; ph ^= 1; }
     }
+    if (elect_one()) tc::mma_commit(&acc_full);
+    __syncwarp();
   } else {
     // ================================ transform ================================
     const int g = warp >> 2;
@@ -140,9 +149,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
     const int a_chunks = ab * (BLK / 16);
     const int b_chunks = bb * (BLK / 16);
     const int b_items = bb * R * 8;                 // (block, row, 16-byte chunk) positions, all channels each
-    for (int it = g; it < nsteps; it += DW_GROUPS) {
-      const int s = it % STG;
-      const uint32_t ph = (uint32_t)(it / STG) & 1;
+    int s = g;                                      // g < groups <= stages
+    uint32_t ph = 0;
+    for (int it = g; it < (g < a.groups ? nsteps : 0); it += a.groups) {
       uint8_t* st = smem + (size_t)s * STAGE_BYTES;
       const int64_t row0 = r_begin + (int64_t)it * R;
       tc::bounded_wait(&raw_full[s], ph);
@@ -202,6 +211,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
       }
       tc::fence_proxy_async();
       mbar_arrive(&ops_ready[s]);
+      s += a.groups;
+      if (s >= STG) { s -= STG; ph ^= 1; }
     }
 
     // ================================ epilogue: accumulators -> partial[split] ================================
@@ -250,38 +261,57 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
 
 // ---- host: pass / split plan -------------------------------------------------------------------
 struct DwPlan {
-  int r, e, nt, mt, ntl, passes_n, passes_k, stages, splits;
+  int r, e, nt, mt, ntl, passes_n, passes_k, stages, groups, splits;
   int64_t rows_per_split;
   int64_t chunks, rows_per_chunk;     // column-sum scratch of pcfd_dw_finish
 };
 
-static inline int dw_rows_per_stage(int cj) { return cj == 1 ? 16 : (cj == 4 ? 4 : 8); }
+// rows per stage: the small value keeps wide tiles within shared memory, the large one amortises the
+// per-stage barrier round trips of narrow layers
+static inline int dw_rows_small(int cj) { return cj == 1 ? 16 : (cj == 4 ? 4 : 8); }
+static inline int dw_rows_large(int cj) { return cj == 1 ? 64 : (cj <= 4 ? 16 : 8); }
+
+// a waiter may only be one phase away from its barrier: the transform group of iteration `it` must also be
+// the group of iteration `it - stages`, so the number of groups in use divides the ring depth
+static inline void dw_ring(int fit, int* stages, int* groups) {
+  if (fit >= 8) { *stages = 8; *groups = 4; }
+  else if (fit >= 6) { *stages = 6; *groups = 3; }
+  else if (fit >= 4) { *stages = 4; *groups = 4; }
+  else { *stages = fit; *groups = fit; }
+}
 
 static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n) {
   DwPlan p;
-  p.r = dw_rows_per_stage(cj);
-  p.e = cj * p.r;
   p.nt = k <= 64 ? 64 : 128;
-  const int blk = p.e * 128;
   const int mt_all = (n + 127) / 128, ntl_all = (k + p.nt - 1) / p.nt;
+  static int force_r = -1;
+  if (force_r < 0) { const char* e = getenv("PCFD_DW_R"); force_r = e ? atoi(e) : 0; }
   double best = 1e300;
-  p.mt = 1; p.ntl = 1; p.stages = 0;
+  p.mt = 1; p.ntl = 1; p.stages = 0; p.groups = 0; p.r = dw_rows_small(cj);
   for (int mt = 1; mt <= mt_all && mt <= 4; ++mt) {
     for (int ntl = 1; ntl <= ntl_all && mt * ntl * p.nt <= 512; ++ntl) {
-      const int stage_bytes = 2 * (mt * 4 + ntl * p.nt / 32) * blk;
-      int stages = DW_SMEM_MAX / stage_bytes;
-      if (stages < 2) continue;
-      if (stages > DW_MAX_STAGES) stages = DW_MAX_STAGES;
-      const int pn = (mt_all + mt - 1) / mt, pk = (ntl_all + ntl - 1) / ntl;
-      // HBM traffic of the operands (each pass along k re-reads gzout, each pass along n re-reads zin);
-      // fewer than 3 stages cannot cover the TMA -> transform -> MMA latency chain
-      double cost = (double)n * pk + (double)k * pn;
-      if (stages < 3) cost *= 1.5;
-      if (cost < best - 1e-9 || (cost < best + 1e-9 && stages > p.stages)) {
-        best = cost; p.mt = mt; p.ntl = ntl; p.stages = stages; p.passes_n = pn; p.passes_k = pk;
+      for (int big = 0; big < 2; ++big) {
+        const int r = big ? dw_rows_large(cj) : dw_rows_small(cj);
+        if (big && r == dw_rows_small(cj)) continue;
+        if (force_r == 1 && big) continue;
+        const int stage_bytes = 2 * (mt * 4 + ntl * p.nt / 32) * (cj * r * 128);
+        int stages = 0, groups = 0;
+        dw_ring(DW_SMEM_MAX / stage_bytes, &stages, &groups);
+        if (stages < 2) continue;
+        if (big && stages < 3 && force_r != 2) continue;
+        const int pn = (mt_all + mt - 1) / mt, pk = (ntl_all + ntl - 1) / ntl;
+        // HBM traffic of the operands (each pass along k re-reads gzout, each pass along n re-reads zin);
+        // fewer than 3 stages cannot cover the TMA -> transform -> MMA latency chain
+        double cost = (double)n * pk + (double)k * pn;
+        if (stages < 3) cost *= 1.5;
+        if (big) cost *= 0.999;                                  // same traffic: prefer the longer stage
+        if (cost < best - 1e-9) {
+          best = cost; p.mt = mt; p.ntl = ntl; p.stages = stages; p.groups = groups; p.passes_n = pn; p.passes_k = pk; p.r = r;
+        }
       }
     }
   }
+  p.e = cj * p.r;
   const int passes = p.passes_n * p.passes_k;
   int64_t splits = num_sms() / passes;
   if (splits < 1) splits = 1;
@@ -315,6 +345,7 @@ static int launch_dw(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
   }
   const int stage_bytes = 2 * (p.mt * 4 + p.ntl * NT / 32) * (CJ * R * 128);
   const int smem = p.stages * stage_bytes + 1024;
+  if (smem > DW_SMEM_MAX + 1024) return PCFD_ERR_ARG;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(ws_dw_kernel<CJ, R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_MAX + 1024);
@@ -358,18 +389,19 @@ extern "C" int pcfd_ws_jet_linear_bwd_dw_partials(const float* gzout, int64_t gz
   if (p.stages < 2) return PCFD_ERR_ARG;
   if (cj == 1) { gzout_ps = (int64_t)rows * ldgzout; zin_ps = (int64_t)rows * ldzin; }
   ws::DwArgs a{reinterpret_cast<float*>(workspace), rows, rows_per_geom, p.rows_per_split, k, n, make_intrans(tin, k),
-               p.mt, p.ntl, p.passes_k, p.stages, (k % 4 == 0 && al16(workspace)) ? 1 : 0};
+               p.mt, p.ntl, p.passes_k, p.stages, p.groups, (k % 4 == 0 && al16(workspace)) ? 1 : 0};
   *splits_out = p.splits;
   cudaStream_t st = (cudaStream_t)stream;
 #define PCFD_WS_DW(CJ_, R_)                                                                                    \
-  return p.nt == 64 ? ws::launch_dw<CJ_, R_, 64>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st)       \
-                    : ws::launch_dw<CJ_, R_, 128>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st);
+  if (p.r == R_)                                                                                               \
+    return p.nt == 64 ? ws::launch_dw<CJ_, R_, 64>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st)     \
+                      : ws::launch_dw<CJ_, R_, 128>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st);
   switch (cj) {
-    case 1: PCFD_WS_DW(1, 16)
-    case 3: PCFD_WS_DW(3, 8)
-    case 4: PCFD_WS_DW(4, 4)
-    case 5: PCFD_WS_DW(5, 8)
-    case 7: PCFD_WS_DW(7, 8)
+    case 1: PCFD_WS_DW(1, 16) PCFD_WS_DW(1, 64) break;
+    case 3: PCFD_WS_DW(3, 8) PCFD_WS_DW(3, 16) break;
+    case 4: PCFD_WS_DW(4, 4) PCFD_WS_DW(4, 16) break;
+    case 5: PCFD_WS_DW(5, 8) break;
+    case 7: PCFD_WS_DW(7, 8) break;
   }
 #undef PCFD_WS_DW
   return PCFD_ERR_ARG;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
   __shared__ uint32_t tmem_base_s;
   __shared__ float ge_acc[128];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(&raw_full[s], 1);
@@ -124,16 +124,16 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
 
   if (warp == DX_W_TMA) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int rt = t / a.k_passes, kp = t - rt * a.k_passes;
-        const int row0 = rt * POINTS;
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::bounded_wait(&stage_free[s], ph ^ 1);
-          uint8_t* st = smem + s * STAGE_BYTES;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int rt = t / a.k_passes, kp = t - rt * a.k_passes;
+      const int row0 = rt * POINTS;
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::bounded_wait(&stage_free[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&raw_full[s], TX_BYTES);
           if (CJ == 1) {
             tma_load_3d(st, &tmG, kc * BK, row0, 0, &raw_full[s]);
@@ -146,31 +146,34 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
           for (int cbk = 0; cbk < NT / 32; ++cbk)
             tma_load_2d(st + 2 * A_BYTES + cbk * (BK * 128), &tmW, kp * NT + cbk * 32, kc * BK, &raw_full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == DX_W_MMA) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, true);     // A K-major, B MN-major
-      uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-        const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
-        tc::bounded_wait(&acc_free[buf], aph ^ 1);
+    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, true);     // A K-major, B MN-major
+    const uint64_t abase = desc_kmajor<64>(tc::smem_u32(smem));              // + (byte offset >> 4) in the address field
+    const uint64_t bbase = desc_mnmajor(tc::smem_u32(smem), BK * 128, 512);
+    uint32_t it = 0, tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      tc::bounded_wait(&acc_free[buf], aph ^ 1);
+      tc::tc_fence_after();
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::bounded_wait(&ops_ready[s], ph);
         tc::tc_fence_after();
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::bounded_wait(&ops_ready[s], ph);
-          tc::tc_fence_after();
-          const uint32_t sb = tc::smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t so = (uint64_t)((uint32_t)(s * STAGE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
-            const uint64_t db_hi = desc_mnmajor(sb + 2 * A_BYTES + ks * 1024, BK * 128, 512);
-            const uint64_t db_lo = desc_mnmajor(sb + 2 * A_BYTES + B_BYTES + ks * 1024, BK * 128, 512);
+            const uint64_t db_hi = bbase + so + ((2 * A_BYTES + ks * 1024) >> 4);
+            const uint64_t db_lo = bbase + so + ((2 * A_BYTES + B_BYTES + ks * 1024) >> 4);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const uint64_t da_hi = desc_kmajor<64>(sb + u * 4 * SLAB_BYTES + ks * 32);
-              const uint64_t da_lo = desc_kmajor<64>(sb + A_BYTES + u * 4 * SLAB_BYTES + ks * 32);
+              const uint64_t da_hi = abase + so + ((u * 4 * SLAB_BYTES + ks * 32) >> 4);
+              const uint64_t da_lo = abase + so + ((A_BYTES + u * 4 * SLAB_BYTES + ks * 32) >> 4);
               const uint32_t d = tmem_base + buf * (2 * NT) + u * NT;
               tc::mma_tf32(d, da_hi, db_hi, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
               tc::mma_tf32(d, da_lo, db_hi, IDESC, 1u);
@@ -179,8 +182,10 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
           }
           tc::mma_commit(&stage_free[s]);
         }
-        tc::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (elect_one()) tc::mma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else if (warp < DX_W_TMA) {
     // ================================ operand remainders ================================

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
   __shared__ __align__(8) uint64_t acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(&raw_full[s], 1);
@@ -85,16 +85,16 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
 
   if (warp == W_TMA) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int rt = t / a.n_passes, np = t - rt * a.n_passes;
-        const int row0 = rt * POINTS;
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::bounded_wait(&stage_free[s], ph ^ 1);
-          uint8_t* st = smem + s * STAGE_BYTES;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int rt = t / a.n_passes, np = t - rt * a.n_passes;
+      const int row0 = rt * POINTS;
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::bounded_wait(&stage_free[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&raw_full[s], TX_BYTES);
           if (CJ == 1) {
             tma_load_3d(st, &tmZ, kc * BK, row0, 0, &raw_full[s]);
@@ -105,31 +105,33 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
           }
           tma_load_2d(st + 2 * A_BYTES, &tmW, kc * BK, np * NT, &raw_full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == W_MMA) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, false);
-      uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-        const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
-        tc::bounded_wait(&acc_free[buf], aph ^ 1);
+    constexpr uint32_t IDESC = tc::make_idesc_tf32(128, NT, false, false);
+    const uint64_t dbase = desc_kmajor<64>(tc::smem_u32(smem));      // + (byte offset >> 4) in the address field
+    uint32_t it = 0, tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const uint32_t buf = tl & 1, aph = (tl >> 1) & 1;
+      tc::bounded_wait(&acc_free[buf], aph ^ 1);
+      tc::tc_fence_after();
+      for (int kc = 0; kc < nkc; ++kc, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::bounded_wait(&ops_ready[s], ph);
         tc::tc_fence_after();
-        for (int kc = 0; kc < nkc; ++kc, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          tc::bounded_wait(&ops_ready[s], ph);
-          tc::tc_fence_after();
-          const uint32_t sb = tc::smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t ds = dbase + (uint64_t)((uint32_t)(s * STAGE_BYTES) >> 4);
+        if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < ((a.dbg & 4) ? 0 : BK / 8); ++ks) {
-            const uint64_t db_hi = desc_kmajor<64>(sb + 2 * A_BYTES + ks * 32);
-            const uint64_t db_lo = desc_kmajor<64>(sb + 2 * A_BYTES + B_BYTES + ks * 32);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t db_hi = ds + ((2 * A_BYTES + ks * 32) >> 4);
+            const uint64_t db_lo = ds + ((2 * A_BYTES + B_BYTES + ks * 32) >> 4);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const uint64_t da_hi = desc_kmajor<64>(sb + u * 4 * SLAB_BYTES + ks * 32);
-              const uint64_t da_lo = desc_kmajor<64>(sb + A_BYTES + u * 4 * SLAB_BYTES + ks * 32);
+              const uint64_t da_hi = ds + ((u * 4 * SLAB_BYTES + ks * 32) >> 4);
+              const uint64_t da_lo = ds + ((A_BYTES + u * 4 * SLAB_BYTES + ks * 32) >> 4);
               const uint32_t d = tmem_base + buf * (2 * NT) + u * NT;
               tc::mma_tf32(d, da_hi, db_hi, IDESC, (kc > 0 || ks > 0) ? 1u : 0u);
               tc::mma_tf32(d, da_lo, db_hi, IDESC, 1u);
@@ -138,8 +140,10 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
           }
           tc::mma_commit(&stage_free[s]);
         }
-        tc::mma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (elect_one()) tc::mma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else if (warp < W_TMA) {
     // ================================ transform ================================

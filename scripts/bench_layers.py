@@ -61,8 +61,9 @@ def main():
     tot = {e: {p: 0.0 for p in passes} for e in engines}
     worst = 0.0
     for name, cj, rows, k, n, act, drop in cases:
-        rpg = rows // 2 if rows % 2 == 0 else 0
-        ng = 2 if rpg else 1
+        # 32 geometries per batch as in the bench workload (per-geometry bias / cvec sums scale with it)
+        ng = 32 if rows % 32 == 0 else (2 if rows % 2 == 0 else 1)
+        rpg = rows // ng if ng > 1 else 0
         zin = Jet.empty(cj, rows, k, 'cuda')
         zin.t.normal_()
         gz = Jet.empty(cj, rows, n, 'cuda')
