@@ -14,6 +14,17 @@ int pcfd_ffma_jet_linear_bwd_dw(const float*, int64_t, int32_t, const float*, in
 size_t pcfd_ffma_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
 int pcfd_dw_finish(const float*, int, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t, int64_t,
                    int32_t, int32_t, float*, void*);
+int pcfd_thin_fwd_kind(const pcfd_intrans_t*, int32_t, int64_t, int32_t, int32_t);
+int pcfd_thin_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
+                             const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
+                             void*);
+int pcfd_thin_dx_kind(const pcfd_intrans_t*, const float*, int32_t, int64_t, int32_t, int32_t);
+int pcfd_thin_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
+                                const pcfd_intrans_t*, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
+                                void*);
+int pcfd_small_rows_supported_dw(const pcfd_intrans_t*, int32_t, int64_t, int32_t, int32_t);
+int pcfd_small_rows_bwd_dw(const float*, int32_t, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t,
+                           int64_t, int32_t, int32_t, void*);
 #ifdef PCFD_HAVE_TC
 int pcfd_tc_supported_bwd(int32_t cj, int64_t rows, int32_t k, int32_t n);
 int pcfd_tc_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
@@ -92,6 +103,10 @@ extern "C" int pcfd_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t ldz
   if (g_engine == 2 && pcfd_ws_supported_fwd(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, cj, rows, k, n))
     return pcfd_ws_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
                                   rows_per_geom, k, n, stream);
+  // shapes a tensor-core tile cannot use: last layer (n <= 8), first layer (k <= 16), per-geometry rows (<= 32)
+  if (g_engine >= 1 && pcfd_thin_fwd_kind(tin, cj, rows, k, n) >= 0 && (n <= 8 || rows <= 32 || k < 8 || g_engine == 2))
+    return pcfd_thin_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
+                                    rows_per_geom, k, n, stream);
   if (g_engine == 1 && pcfd_tc_supported_fwd(cj, rows, k, n, ldzin, ldw, ldzout))
     return pcfd_tc_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,
                                   rows_per_geom, k, n, stream);
@@ -112,6 +127,9 @@ extern "C" int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int3
   int rc = ensure_arch();
   if (rc) return rc;
 #ifdef PCFD_HAVE_TC
+  if (g_engine >= 1 && pcfd_thin_dx_kind(tin, gescale, cj, rows, k, n) >= 0)
+    return pcfd_thin_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin, cj,
+                                       rows, rows_per_geom, k, n, stream);
   if (g_engine == 2 && pcfd_ws_supported_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, gzin, gzin_ps, ldgzin, cj,
                                             rows, k, n))
     return pcfd_ws_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
@@ -136,6 +154,9 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
   int rc = ensure_arch();
   if (rc) return rc;
   if (workspace_bytes < pcfd_jet_linear_bwd_dw_workspace_bytes(cj, rows, rows_per_geom, k, n)) return PCFD_ERR_WORKSPACE;
+  if (g_engine >= 1 && pcfd_small_rows_supported_dw(tin, cj, rows, k, n))
+    return pcfd_small_rows_bwd_dw(gzout, ldgzout, zin, ldzin, gw, ldgw, gbias, gcvec, ldgcvec, rows, rows_per_geom, k, n,
+                                  stream);
 #ifdef PCFD_HAVE_TC
   if (g_engine == 2 && gw != nullptr && pcfd_ws_supported_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, cj, rows, k, n)) {
     int splits = 0;

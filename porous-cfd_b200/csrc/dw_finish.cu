@@ -1,0 +1,146 @@
+// Shared tail of every dW engine: fixed-order (deterministic) reduction of the row-split partial products into
+// the weight gradient, and the column sums of the value plane of gzout that form the bias gradient and the
+// per-geometry constant ("cvec") gradient.
+//
+//   colsum_kernel   tmp[chunk][sub][n] = sum over the CS_ROWS rows of a sub-block of gzout[0][row][:]
+//                   (a chunk is one geometry, or 2048 rows when the layer has no per-geometry term); HBM-bound,
+//                   16-byte loads, 128 columns x 8 row lanes per CTA
+//   finish_kernel   one launch, two block roles:
+//                     gw[n][k]   += sum_split partial[split][n][k]            (8 split lanes per element)
+//                     gcvec[c][:] += sum_sub tmp[c][sub][:],  gbias += sum_c  (8 chunk lanes per column)
+#include "common.cuh"
+
+namespace pcfd {
+
+constexpr int CS_ROWS = 512;
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ldg, int64_t rows,
+                                                     int64_t rows_per_chunk, int subs, int n, float* tmp, int vec) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int64_t chunk = blockIdx.x / subs, sub = blockIdx.x % subs;
+  const int64_t c_begin = chunk * rows_per_chunk;
+  const int64_t c_end = min(rows, c_begin + rows_per_chunk);
+  const int64_t r_begin = c_begin + sub * CS_ROWS;
+  const int64_t r_end = min(c_end, r_begin + CS_ROWS);
+  const int col = blockIdx.y * 128 + lane * 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec && col + 4 <= n) {
+    int64_t r = r_begin + wy;
+    for (; r + 24 < r_end; r += 32) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g + r * ldg + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(g + (r + 8) * ldg + col));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(g + (r + 16) * ldg + col));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(g + (r + 24) * ldg + col));
+      s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+      s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r_end; r += 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g + r * ldg + col));
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  } else if (col < n) {
+    for (int64_t r = r_begin + wy; r < r_end; r += 8) {
+      const float* p = g + r * ldg + col;
+      s.x += __ldg(p);
+      if (col + 1 < n) s.y += __ldg(p + 1);
+      if (col + 2 < n) s.z += __ldg(p + 2);
+      if (col + 3 < n) s.w += __ldg(p + 3);
+    }
+  }
+  red[wy][lane] = s;
+  __syncthreads();
+  if (wy == 0 && col < n) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { const float4 v = red[i][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    float* o = tmp + (int64_t)blockIdx.x * n + col;
+    o[0] = t.x;
+    if (col + 1 < n) o[1] = t.y;
+    if (col + 2 < n) o[2] = t.z;
+    if (col + 3 < n) o[3] = t.w;
+  }
+}
+
+__global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict__ partial, int splits, int n, int k,
+                                                        float* gw, int ldgw, int gw_blocks,
+                                                        const float* __restrict__ tmp, int64_t chunks, int subs,
+                                                        float* gbias, float* gcvec, int ldgcvec) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  if ((int)blockIdx.x < gw_blocks) {
+    // ---- weight gradient: element = blockIdx.x * 32 + lane, split lane wy
+    const int64_t total = (int64_t)n * k;
+    const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
+    float s = 0.0f;
+    if (idx < total) {
+      int sp = wy;
+      for (; sp + 8 < splits; sp += 16) s += partial[(int64_t)sp * total + idx] + partial[(int64_t)(sp + 8) * total + idx];
+      for (; sp < splits; sp += 8) s += partial[(int64_t)sp * total + idx];
+    }
+    red[wy][lane] = s;
+    __syncthreads();
+    if (wy == 0 && idx < total) {
+      float t = red[0][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) t += red[i][lane];
+      const int nn = (int)(idx / k), kk = (int)(idx - (int64_t)nn * k);
+      gw[(int64_t)nn * ldgw + kk] += t;
+    }
+    return;
+  }
+  // ---- column sums: column = (blockIdx.x - gw_blocks) * 32 + lane, chunk lane wy
+  const int col = ((int)blockIdx.x - gw_blocks) * 32 + lane;
+  float s = 0.0f;
+  if (col < n) {
+    for (int64_t c = wy; c < chunks; c += 8) {
+      const float* p = tmp + c * subs * n + col;
+      float v = 0.0f;
+      for (int u = 0; u < subs; ++u) v += p[(int64_t)u * n];
+      s += v;
+      if (gcvec != nullptr) gcvec[c * ldgcvec + col] += v;
+    }
+  }
+  red[wy][lane] = s;
+  __syncthreads();
+  if (wy == 0 && col < n && gbias != nullptr) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    gbias[col] += t;
+  }
+}
+
+}  // namespace pcfd
+
+using namespace pcfd;
+
+// tmp must hold chunks * ceil(rows_per_chunk / CS_ROWS) * n floats (every engine's workspace query reserves
+// chunks * ceil(rows_per_chunk / 128) * n)
+extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzout, int32_t ldgzout, float* gw,
+                              int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int64_t rows,
+                              int64_t rows_per_geom, int32_t k, int32_t n, float* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool do_gw = gw != nullptr && partial != nullptr;
+  const bool do_cs = gbias != nullptr || gcvec != nullptr;
+  int64_t chunks = 0;
+  int subs = 0;
+  if (do_cs) {
+    if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
+    const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
+    chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    subs = (int)((rows_per_chunk + CS_ROWS - 1) / CS_ROWS);
+    const int vec = (reinterpret_cast<uintptr_t>(gzout) & 15) == 0 && ldgzout % 4 == 0;
+    dim3 grid((unsigned)(chunks * subs), (unsigned)((n + 127) / 128));
+    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, subs, n, tmp, vec);
+    PCFD_CHECK_LAUNCH();
+  }
+  if (do_gw || do_cs) {
+    const int gw_blocks = do_gw ? (int)(((int64_t)n * k + 31) / 32) : 0;
+    const int cs_blocks = do_cs ? (n + 31) / 32 : 0;
+    dw_finish_kernel<<<(unsigned)(gw_blocks + cs_blocks), 256, 0, st>>>(partial, splits, n, k, gw, ldgw, gw_blocks, tmp,
+                                                                        chunks, subs, gbias, gcvec, ldgcvec);
+    PCFD_CHECK_LAUNCH();
+  }
+  return PCFD_OK;
+}

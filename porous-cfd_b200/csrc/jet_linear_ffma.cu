@@ -395,56 +395,6 @@ __global__ void __launch_bounds__(256) jet_dw_kernel(DwArgs a) {
   }
 }
 
-__global__ void dw_reduce_kernel(const float* __restrict__ partial, int splits, int n, int k, float* gw, int ldgw) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)n * k) return;
-  float s = 0.0f;
-  for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * n * k + idx];
-  const int nn = (int)(idx / k), kk = (int)(idx % k);
-  gw[(int64_t)nn * ldgw + kk] += s;
-}
-
-// column sums of plane 0 of gzout: each chunk (a geometry, or 2048 rows) is cut into sub-blocks of
-// CS_ROWS rows so that the grid fills the GPU; tmp[chunk][sub][n], reduced in fixed order below.
-constexpr int CS_ROWS = 128;
-
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ldg, int64_t rows,
-                                                     int64_t rows_per_chunk, int subs, int n, float* tmp) {
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int col = blockIdx.y * 32 + lane;
-  const int64_t chunk = blockIdx.x / subs, sub = blockIdx.x % subs;
-  const int64_t c_begin = chunk * rows_per_chunk;
-  const int64_t c_end = min(rows, c_begin + rows_per_chunk);
-  const int64_t r_begin = c_begin + sub * CS_ROWS;
-  const int64_t r_end = min(c_end, r_begin + CS_ROWS);
-  float s = 0.0f;
-  if (col < n)
-    for (int64_t r = r_begin + wy; r < r_end; r += 8) s += __ldg(g + r * ldg + col);
-  red[wy][lane] = s;
-  __syncthreads();
-  if (wy == 0 && col < n) {
-    float t = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][lane];
-    tmp[(int64_t)blockIdx.x * n + col] = t;
-  }
-}
-
-__global__ void colsum_finish_kernel(const float* __restrict__ tmp, int64_t chunks, int subs, int n, float* gbias,
-                                     float* gcvec, int ldgcvec) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= n) return;
-  float s = 0.0f;
-  for (int64_t c = 0; c < chunks; ++c) {
-    float v = 0.0f;
-    for (int u = 0; u < subs; ++u) v += tmp[(c * subs + u) * n + col];
-    s += v;
-    if (gcvec != nullptr) gcvec[c * ldgcvec + col] += v;
-  }
-  if (gbias != nullptr) gbias[col] += s;
-}
-
 // ---------------------------------------------------------------------------------------------
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -527,30 +477,8 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps,
   return PCFD_ERR_ARG;
 }
 
-// Shared tail of both engines' dW: fixed-order reduction of the row-split partials into gw (+=), and the
-// per-geometry column sums of the value plane for the bias / per-geometry-constant gradients.
-extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzout, int32_t ldgzout, float* gw,
-                              int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int64_t rows,
-                              int64_t rows_per_geom, int32_t k, int32_t n, float* tmp, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (gw != nullptr && partial != nullptr) {
-    const int64_t total = (int64_t)n * k;
-    dw_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, splits, n, k, gw, ldgw);
-    PCFD_CHECK_LAUNCH();
-  }
-  if (gbias != nullptr || gcvec != nullptr) {
-    if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
-    const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
-    const int64_t chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
-    const int subs = (int)((rows_per_chunk + CS_ROWS - 1) / CS_ROWS);
-    dim3 grid((unsigned)(chunks * subs), (unsigned)((n + 31) / 32));
-    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, subs, n, tmp);
-    PCFD_CHECK_LAUNCH();
-    colsum_finish_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(tmp, chunks, subs, n, gbias, gcvec, ldgcvec);
-    PCFD_CHECK_LAUNCH();
-  }
-  return PCFD_OK;
-}
+extern "C" int pcfd_dw_finish(const float*, int, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t,
+                              int64_t, int32_t, int32_t, float*, void*);   // dw_finish.cu
 
 extern "C" size_t pcfd_ffma_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   if (!valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0) return 0;

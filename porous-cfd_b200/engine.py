@@ -387,10 +387,12 @@ class PinnExecutor:
         ctx.training = self.model.training
         b, n, d = points.shape
         points = points.detach().contiguous().float()
+        ops.begin_step()
         cvecs, escale, _ = self._encode(data, labels, domain, None, None, points)
         z0 = Jet.empty(1, b * n, d, data.device)
         ops.gather_cols(points, b, n, d, None, 0, n, list(range(d)), z0.t, z0.ld, n)
         zs = chain_forward(ctx, plan['point_layers'], z0, n, escale, cvecs, salt_base=100)
+        ops.end_step()
         return zs[-1].values().reshape(b, n, d + 1)
 
     def step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
@@ -411,6 +413,7 @@ class PinnExecutor:
         cj = 1 + d if laplacian == 'reference' else 1 + 2 * d
         c_cols = self._cols(labels, 'C')
 
+        ops.begin_step()
         ops.zero_(self.flat_grad)
         if ctx.training:
             ops.advance_seed(ctx.seed_dev)
@@ -436,6 +439,7 @@ class PinnExecutor:
         chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100)
         chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200)
         self._encode_backward(saved, gcvecs, gescale)
+        ops.end_step()
 
         n_terms = 2 * d + 2 + ((d + 1) if obs_ids is not None else 0)
         res = StepResult(out, n_terms)

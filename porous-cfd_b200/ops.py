@@ -109,15 +109,53 @@ class Jet:
         return self.t[0, :, :self.width]
 
 
+# The TMA-fed engine needs 16-byte aligned weight rows.  Reference parameter shapes such as [64, 10] or
+# [128, 131] (set-abstraction MLPs, models/modules.py:506-512) are not, so the step keeps a zero-padded copy of
+# those few weight blocks, refreshed once per step by one device copy (inside the captured graph).
+_WPAD: dict = {}
+_WPAD_FRESH: set = set()
+_IN_STEP = False
+
+
+def begin_step() -> None:
+    """Weights do not change until end_step(): padded copies made from here on are reused."""
+    global _IN_STEP
+    _WPAD_FRESH.clear()
+    _IN_STEP = True
+
+
+def end_step() -> None:
+    global _IN_STEP
+    _WPAD_FRESH.clear()
+    _IN_STEP = False
+
+
+def _weight_block(w: Tensor, col_lo: int, k: int, n: int):
+    if k < 8 or (w.stride(0) % 4 == 0 and col_lo % 4 == 0 and w.data_ptr() % 16 == 0):
+        return w.data_ptr() + 4 * col_lo, w.stride(0)
+    key = (w.data_ptr(), col_lo, k, n)
+    buf = _WPAD.get(key)
+    if buf is None:
+        buf = torch.zeros((n, round4(k)), dtype=torch.float32, device=w.device)
+        _WPAD[key] = buf
+    if key not in _WPAD_FRESH:
+        buf[:, :k].copy_(w.detach()[:, col_lo:col_lo + k])
+        if _IN_STEP:
+            _WPAD_FRESH.add(key)
+        _lib.launches += 1
+    return buf.data_ptr(), buf.stride(0)
+
+
 def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: int, bias: Optional[Tensor],
                    cvec: Optional[Tensor], rows_per_geom: int, n: int, out: Optional[Jet] = None) -> Jet:
     lib = _lib.load()
     if out is None:
         out = Jet.empty(zin.cj, zin.rows, n, zin.t.device)
     _lib.launches += 1
+    wptr, ldw = _weight_block(w, col_lo, k, n)
     with _timed(f'jet_fwd_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
       check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
-                                  w.data_ptr() + 4 * col_lo, w.stride(0), _ptr(bias), _ptr(cvec),
+                                  wptr, ldw, _ptr(bias), _ptr(cvec),
                                   cvec.stride(0) if cvec is not None else 0,
                                   out.t.data_ptr(), out.plane_stride, out.ld, zin.cj, zin.rows, rows_per_geom, k, n,
                                   _stream()), 'pcfd_jet_linear_fwd')
@@ -129,9 +167,10 @@ def jet_linear_bwd_dx(gzout: Jet, w: Tensor, col_lo: int, zin: Jet, tin: Optiona
     lib = _lib.load()
     gzin = Jet.empty(zin.cj, zin.rows, k, zin.t.device)
     _lib.launches += 1
+    wptr, ldw = _weight_block(w, col_lo, k, n)
     with _timed(f'jet_dx_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
-      check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, w.data_ptr() + 4 * col_lo,
-                                     w.stride(0), zin.t.data_ptr(), zin.plane_stride, zin.ld,
+      check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, wptr,
+                                     ldw, zin.t.data_ptr(), zin.plane_stride, zin.ld,
                                      C.byref(tin) if tin is not None else None,
                                      gzin.t.data_ptr(), gzin.plane_stride, gzin.ld, _ptr(gescale),
                                      gescale.stride(0) if gescale is not None else 0,
@@ -147,7 +186,7 @@ def jet_linear_bwd_dw(gzout: Jet, zin: Jet, tin: Optional[InTrans], gw: Optional
                       gbias: Optional[Tensor], gcvec: Optional[Tensor], rows_per_geom: int, k: int, n: int,
                       workspace: Tensor) -> None:
     lib = _lib.load()
-    _lib.launches += 2 + (2 if (gbias is not None or gcvec is not None) else 0)
+    _lib.launches += 2 + (1 if (gbias is not None or gcvec is not None) else 0)
     with _timed(f'jet_dw_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
       check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
                                      zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
