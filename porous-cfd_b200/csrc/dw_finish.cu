@@ -2,7 +2,7 @@
 // the weight gradient, and the column sums of the value plane of gzout that form the bias gradient and the
 // per-geometry constant ("cvec") gradient.
 //
-//   colsum_kernel   tmp[chunk][sub][n] = sum over the CS_ROWS rows of a sub-block of gzout[0][row][:]
+//   colsum_kernel   tmp[chunk][sub][n] = sum over the rows of a sub-block (128..512) of gzout[0][row][:]
 //                   (a chunk is one geometry, or 2048 rows when the layer has no per-geometry term); HBM-bound,
 //                   16-byte loads, 128 columns x 8 row lanes per CTA
 //   finish_kernel   one launch, two block roles:
@@ -12,17 +12,17 @@
 
 namespace pcfd {
 
-constexpr int CS_ROWS = 512;
+constexpr int CS_ROWS_MAX = 512, CS_ROWS_MIN = 128;   // workspace queries reserve tmp for 128-row sub-blocks
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int ldg, int64_t rows,
-                                                     int64_t rows_per_chunk, int subs, int n, float* tmp, int vec) {
+                                                     int64_t rows_per_chunk, int subs, int cs_rows, int n, float* tmp, int vec) {
   __shared__ float4 red[8][32];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int64_t chunk = blockIdx.x / subs, sub = blockIdx.x % subs;
   const int64_t c_begin = chunk * rows_per_chunk;
   const int64_t c_end = min(rows, c_begin + rows_per_chunk);
-  const int64_t r_begin = c_begin + sub * CS_ROWS;
-  const int64_t r_end = min(c_end, r_begin + CS_ROWS);
+  const int64_t r_begin = c_begin + sub * cs_rows;
+  const int64_t r_end = min(c_end, r_begin + cs_rows);
   const int col = blockIdx.y * 128 + lane * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (vec && col + 4 <= n) {
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
 
 using namespace pcfd;
 
-// tmp must hold chunks * ceil(rows_per_chunk / CS_ROWS) * n floats (every engine's workspace query reserves
+// tmp must hold chunks * ceil(rows_per_chunk / 128) * n floats (every engine's workspace query reserves
 // chunks * ceil(rows_per_chunk / 128) * n)
 extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzout, int32_t ldgzout, float* gw,
                               int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int64_t rows,
@@ -129,10 +129,13 @@ extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzo
     if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
     const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
-    subs = (int)((rows_per_chunk + CS_ROWS - 1) / CS_ROWS);
+    // long sub-blocks amortise the block reduction, but small problems need enough CTAs to hide the load latency
+    int cs_rows = CS_ROWS_MAX;
+    while (cs_rows > CS_ROWS_MIN && chunks * ((rows_per_chunk + cs_rows - 1) / cs_rows) * ((n + 127) / 128) < 4 * 148) cs_rows >>= 1;
+    subs = (int)((rows_per_chunk + cs_rows - 1) / cs_rows);
     const int vec = (reinterpret_cast<uintptr_t>(gzout) & 15) == 0 && ldgzout % 4 == 0;
     dim3 grid((unsigned)(chunks * subs), (unsigned)((n + 127) / 128));
-    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, subs, n, tmp, vec);
+    colsum_kernel<<<grid, 256, 0, st>>>(gzout, ldgzout, rows, rows_per_chunk, subs, cs_rows, n, tmp, vec);
     PCFD_CHECK_LAUNCH();
   }
   if (do_gw || do_cs) {

@@ -263,68 +263,43 @@ __global__ void __launch_bounds__(256) thin_k_fwd_kernel(ThinFwdArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // small_rows (rows <= 32, cj = 1, no input transform)
 // ---------------------------------------------------------------------------------------------------------------
-// forward: one warp per output column
-__global__ void __launch_bounds__(256) small_rows_fwd_kernel(const float* __restrict__ zin, int ldzin,
-                                                             const float* __restrict__ w, int ldw, const float* bias,
-                                                             const float* cvec, int ldcvec, float* zout, int ldzout,
-                                                             int rows, int64_t rows_per_geom, int k, int n) {
+// forward and dX share one kernel: out[r][c] = sum_j x[r][j] * W(c, j)  with W(c, j) = w[c*ldw + j] (forward: c = output
+// column, j = input) or w[j*ldw + c] (dX: c = input column, j = output).  One CTA = 8 output columns (one warp
+// each) x all rows (lane = row); the contraction is tiled through shared memory in steps of 128, so there are no
+// shuffles and every global load is issued by all 256 threads at once.
+template <bool TRANSPOSED_W>
+__global__ void __launch_bounds__(256) small_rows_kernel(const float* __restrict__ x, int ldx,
+                                                         const float* __restrict__ w, int ldw, const float* bias,
+                                                         const float* cvec, int ldcvec, float* out, int ldout, int rows,
+                                                         int64_t rows_per_geom, int kdim, int ncols) {
+  __shared__ float xs[32][129];
+  __shared__ float wt[8][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= n) return;
-  float acc[32];
-#pragma unroll
-  for (int r = 0; r < 32; ++r) acc[r] = 0.0f;
-  for (int kk = lane; kk < k; kk += 32) {
-    const float wv = __ldg(w + (int64_t)j * ldw + kk);
-#pragma unroll
-    for (int r = 0; r < 32; ++r)
-      if (r < rows) acc[r] = fmaf(__ldg(zin + (int64_t)r * ldzin + kk), wv, acc[r]);
-  }
-  float val = 0.0f;
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    if (r < rows) {
-      float t = acc[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      val = lane == r ? t : val;
+  const int c0 = blockIdx.x * 8;
+  float acc = 0.0f;
+  for (int j0 = 0; j0 < kdim; j0 += 128) {
+    for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+      const int r = i >> 7, jj = i & 127;
+      xs[r][jj] = (r < rows && j0 + jj < kdim) ? __ldg(x + (int64_t)r * ldx + j0 + jj) : 0.0f;
     }
-  }
-  if (lane < rows) {
-    if (bias != nullptr) val += __ldg(bias + j);
-    if (cvec != nullptr) val += __ldg(cvec + geom_of(lane, rows_per_geom) * ldcvec + j);
-    zout[(int64_t)lane * ldzout + j] = val;
-  }
-}
-
-// dX: 32 input columns x 8 contraction lanes per CTA
-__global__ void __launch_bounds__(256) small_rows_dx_kernel(const float* __restrict__ gz, int ldgz,
-                                                            const float* __restrict__ w, int ldw, float* gzin,
-                                                            int ldgzin, int rows, int k, int n) {
-  __shared__ float red[8][32][33];
-  const int lane = threadIdx.x & 31, nl = threadIdx.x >> 5;
-  const int kk = blockIdx.x * 32 + lane;
-  float acc[32];
-#pragma unroll
-  for (int r = 0; r < 32; ++r) acc[r] = 0.0f;
-  for (int j = nl; j < n; j += 8) {
-    const float wv = kk < k ? __ldg(w + (int64_t)j * ldw + kk) : 0.0f;
-#pragma unroll
-    for (int r = 0; r < 32; ++r)
-      if (r < rows) acc[r] = fmaf(__ldg(gz + (int64_t)r * ldgz + j), wv, acc[r]);
-  }
-#pragma unroll
-  for (int r = 0; r < 32; ++r) red[nl][r][lane] = acc[r];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = nl * 4 + i;
-    if (r < rows && kk < k) {
-      float t = 0.0f;
-#pragma unroll
-      for (int l = 0; l < 8; ++l) t += red[l][r][lane];
-      gzin[(int64_t)r * ldgzin + kk] = t;
+    for (int i = threadIdx.x; i < 8 * 128; i += 256) {
+      int cc, jj;
+      if (TRANSPOSED_W) { cc = i & 7; jj = i >> 3; } else { cc = i >> 7; jj = i & 127; }
+      float v = 0.0f;
+      if (c0 + cc < ncols && j0 + jj < kdim)
+        v = TRANSPOSED_W ? __ldg(w + (int64_t)(j0 + jj) * ldw + c0 + cc) : __ldg(w + (int64_t)(c0 + cc) * ldw + j0 + jj);
+      wt[cc][jj] = v;
     }
+    __syncthreads();
+#pragma unroll 16
+    for (int jj = 0; jj < 128; ++jj) acc = fmaf(xs[lane][jj], wt[warp][jj], acc);
+    __syncthreads();
+  }
+  const int c = c0 + warp;
+  if (lane < rows && c < ncols) {
+    if (bias != nullptr) acc += __ldg(bias + c);
+    if (cvec != nullptr) acc += __ldg(cvec + geom_of(lane, rows_per_geom) * ldcvec + c);
+    out[(int64_t)lane * ldout + c] = acc;
   }
 }
 
@@ -380,8 +355,8 @@ extern "C" int pcfd_thin_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_
   const int kind = pcfd_thin_fwd_kind(tin, cj, rows, k, n);
   if (kind < 0) return PCFD_ERR_ARG;
   if (kind == 2) {
-    small_rows_fwd_kernel<<<(n + 7) / 8, 256, 0, st>>>(zin, ldzin, w, ldw, bias, cvec, ldcvec, zout, ldzout, (int)rows,
-                                                       rows_per_geom, k, n);
+    small_rows_kernel<false><<<(n + 7) / 8, 256, 0, st>>>(zin, ldzin, w, ldw, bias, cvec, ldcvec, zout, ldzout, (int)rows,
+                                                          rows_per_geom, k, n);
     PCFD_CHECK_LAUNCH();
     return PCFD_OK;
   }
@@ -424,7 +399,8 @@ extern "C" int pcfd_thin_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps,
   const int kind = pcfd_thin_dx_kind(tin, nullptr, cj, rows, k, n);
   if (kind < 0) return PCFD_ERR_ARG;
   if (kind == 2) {
-    small_rows_dx_kernel<<<(k + 31) / 32, 256, 0, st>>>(gzout, ldgzout, w, ldw, gzin, ldgzin, (int)rows, k, n);
+    small_rows_kernel<true><<<(k + 7) / 8, 256, 0, st>>>(gzout, ldgzout, w, ldw, nullptr, nullptr, 0, gzin, ldgzin,
+                                                         (int)rows, 0, n, k);
     PCFD_CHECK_LAUNCH();
     return PCFD_OK;
   }

@@ -68,6 +68,58 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ pos
   }
 }
 
+// Register-resident variant for n <= 8192: every thread keeps PPT points (coordinates and running min-distance)
+// in registers, the per-sample arg-max is two redux.sync per warp (max of the distance bits, then min of the
+// indices that attain it -- the same order as the 64-bit key above: largest distance, lowest index) and one
+// barrier across the (few) warps.  ~0.15 us per sample instead of ~0.6 us.
+template <int DIMS, int PPT>
+__global__ void __launch_bounds__(1024) fps_reg_kernel(const float* __restrict__ pos, int n, int m,
+                                                       int64_t* __restrict__ idx_out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem;                 // [n][DIMS] (winner lookup)
+  __shared__ unsigned slot_d[2][32], slot_i[2][32];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const float* gp = pos + (size_t)g * n * DIMS;
+  for (int i = tid; i < n * DIMS; i += nt) sp[i] = gp[i];
+  __syncthreads();
+  float px[PPT][DIMS], md[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int p = tid + i * nt;
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) px[i][d] = p < n ? sp[p * DIMS + d] : 0.0f;
+    md[i] = p < n ? INFINITY : 0.0f;          // padding slots stay at distance 0 with the highest index: never chosen
+  }
+  int cur = 0;
+  if (tid == 0) idx_out[(size_t)g * m] = (int64_t)g * n;
+  for (int s = 1; s < m; ++s) {
+    float c[DIMS];
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) c[d] = sp[cur * DIMS + d];
+    unsigned bd = 0u, bi = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const float d = fminf(md[i], sqdist<DIMS>(px[i], c));
+      md[i] = d;
+      const unsigned db = __float_as_uint(d);
+      const unsigned p = (unsigned)(tid + i * nt);
+      // points of a thread are visited in increasing index: the first maximum wins (also when every distance is 0)
+      if (p < (unsigned)n && (db > bd || bi == 0xffffffffu)) { bd = db; bi = p; }
+    }
+    const unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    const unsigned wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
+    if (lane == 0) { slot_d[s & 1][warp] = wd; slot_i[s & 1][warp] = wi; }
+    __syncthreads();
+    unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
+    unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
+    const unsigned gd = __reduce_max_sync(0xffffffffu, vd);
+    cur = (int)__reduce_min_sync(0xffffffffu, vd == gd ? vi : 0xffffffffu);
+    if (tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + cur;
+  }
+}
+
 // One warp per centroid: scan the geometry's points 32 at a time, keep the first k hits by index.
 template <int DIMS>
 __global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ pos,
@@ -191,9 +243,26 @@ extern "C" int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dim
   if (!pos || !idx_out || n_geom <= 0 || n <= 0 || m <= 0 || m > n || (dims != 2 && dims != 3)) return PCFD_ERR_ARG;
   const size_t smem = (size_t)n * (dims + 1) * sizeof(float);
   if (smem > 220 * 1024) return PCFD_ERR_ARG;   // larger point sets need the clustered variant (not built yet)
-  int threads = n <= 1024 ? 256 : (n <= 4096 ? 512 : 1024);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  if (n <= 8192) {
+    const size_t rsmem = (size_t)n * dims * sizeof(float);
+    const int ppt = 8;
+    int rthreads = (n + ppt - 1) / ppt;
+    rthreads = (rthreads + 31) / 32 * 32;
+    if (rthreads < 32) rthreads = 32;
+#define PCFD_FPS_REG(D_, P_)                                                                                        \
+    {                                                                                                               \
+      e = cudaFuncSetAttribute(fps_reg_kernel<D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);    \
+      if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;                                                          \
+      fps_reg_kernel<D_, P_><<<n_geom, rthreads, rsmem, st>>>(pos, n, m, idx_out);                                  \
+    }
+    if (dims == 2) PCFD_FPS_REG(2, 8) else PCFD_FPS_REG(3, 8)
+#undef PCFD_FPS_REG
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
+  int threads = n <= 1024 ? 256 : (n <= 4096 ? 512 : 1024);
   if (dims == 2) {
     e = cudaFuncSetAttribute(fps_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;

@@ -60,6 +60,62 @@ __global__ void __launch_bounds__(256) segmax_bwd_kernel(const float* __restrict
   }
 }
 
+// Short segments (set-abstraction neighbourhoods: K+1 = 17 .. 65 slots): one warp per (segment, 128 features), 16-byte
+// loads, the slot loop runs in registers -- no shared memory, no barrier.  Ties resolve to the lowest slot as above.
+__global__ void __launch_bounds__(256) segmax_short_fwd_kernel(const float* __restrict__ z, int ldz, int act,
+                                                               const int32_t* __restrict__ slots, int64_t n_seg,
+                                                               int seg_len, int c, float* __restrict__ out, int ldout,
+                                                               int32_t* __restrict__ arg) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int col = blockIdx.y * 128 + lane * 4;
+  if (col >= c) return;
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4] = {-1, -1, -1, -1};
+  const float* base = z + seg * (int64_t)seg_len * ldz + col;
+  for (int j = 0; j < seg_len; ++j) {
+    if (slots != nullptr && __ldg(slots + seg * seg_len + j) < 0) continue;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * ldz));
+    const float v[4] = {act_value(act, x.x), act_value(act, x.y), act_value(act, x.z), act_value(act, x.w)};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (v[e] > best[e] || bi[e] < 0) { best[e] = v[e]; bi[e] = j; }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (col + e < c) {
+      out[seg * ldout + col + e] = bi[e] >= 0 ? best[e] : 0.0f;
+      arg[seg * c + col + e] = bi[e];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) segmax_short_bwd_kernel(const float* __restrict__ gout, int ldgout,
+                                                               const int32_t* __restrict__ arg,
+                                                               const float* __restrict__ z, int ldz, int act,
+                                                               int64_t n_seg, int seg_len, int c,
+                                                               float* __restrict__ gz, int ldgz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int col = blockIdx.y * 128 + lane * 4;
+  if (col >= c) return;
+  int a[4];
+  float g[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    a[e] = col + e < c ? __ldg(arg + seg * c + col + e) : -1;
+    g[e] = col + e < c ? __ldg(gout + seg * ldgout + col + e) : 0.0f;
+    if (a[e] >= 0) g[e] *= act_d1(act, __ldg(z + (seg * (int64_t)seg_len + a[e]) * ldz + col + e));
+  }
+  for (int j = 0; j < seg_len; ++j) {
+    const int64_t row = seg * (int64_t)seg_len + j;
+    *reinterpret_cast<float4*>(gz + row * ldgz + col) =
+        make_float4(j == a[0] ? g[0] : 0.0f, j == a[1] ? g[1] : 0.0f, j == a[2] ? g[2] : 0.0f, j == a[3] ? g[3] : 0.0f);
+  }
+}
+
 }  // namespace pcfd
 
 using namespace pcfd;
@@ -67,6 +123,12 @@ using namespace pcfd;
 extern "C" int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots, int64_t n_seg,
                                int32_t seg_len, int32_t c, float* out, int32_t ldout, int32_t* arg, void* stream) {
   if (!z || !out || !arg || n_seg <= 0 || seg_len <= 0 || c <= 0) return PCFD_ERR_ARG;
+  if (seg_len <= 96 && ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
+    dim3 sgrid((unsigned)((n_seg + 7) / 8), (unsigned)((c + 127) / 128));
+    segmax_short_fwd_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg);
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
   dim3 grid((unsigned)n_seg, (unsigned)((c + 31) / 32));
   segmax_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg);
   PCFD_CHECK_LAUNCH();
@@ -77,6 +139,13 @@ extern "C" int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t*
                                int32_t act, int64_t n_seg, int32_t seg_len, int32_t c, float* gz, int32_t ldgz,
                                void* stream) {
   if (!gout || !arg || !z || !gz || n_seg <= 0 || seg_len <= 0 || c <= 0) return PCFD_ERR_ARG;
+  if (seg_len <= 96 && ldgz % 4 == 0 && (reinterpret_cast<uintptr_t>(gz) & 15) == 0 && ldgz >= ((c + 3) & ~3)) {
+    dim3 sgrid((unsigned)((n_seg + 7) / 8), (unsigned)((c + 127) / 128));
+    segmax_short_bwd_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>(gout, ldgout, arg, z, ldz, act, n_seg, seg_len, c, gz,
+                                                                     ldgz);
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
   dim3 grid((unsigned)n_seg, (unsigned)((c + 31) / 32));
   segmax_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, ldgout, arg, z, ldz, act, n_seg, seg_len, c, gz, ldgz);
   PCFD_CHECK_LAUNCH();

@@ -30,6 +30,10 @@ ABC = [
     ('sa1 L1 128->256', 1, 68000, 128, 256, 'silu', 0.0),
     ('glob L0 259->256', 1, 4000, 259, 256, None, 0.0),
     ('glob L1 256->1024', 1, 4000, 256, 1024, 'silu', 0.0),
+    ('int first 3->64', 4, 48000, 3, 64, None, 0.0),
+    ('int last 128->4', 4, 48000, 128, 4, 'silu', 0.0),
+    ('bnd last 128->4', 1, 32000, 128, 4, 'silu', 0.0),
+    ('cvec 1024->384', 1, 32, 1024, 384, None, 0.0),
 ]
 OTHERS = [
     ('pigano 176->176', 3, 96000, 176, 176, 'silu', 0.0),
