@@ -23,16 +23,17 @@ class KernelProfile:
     roofline leg).  `work` is the algorithmic FLOP (GEMM families) or byte count of the launch."""
 
     def __init__(self):
-        self.records = []   # (name, start_event, end_event, work)
+        self.records = []   # (name, start_event, end_event, work, bytes)
 
     def summary(self) -> dict:
         torch.cuda.synchronize()
         out = {}
-        for name, a, b, work in self.records:
-            d = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'work': 0.0})
+        for name, a, b, work, nbytes in self.records:
+            d = out.setdefault(name, {'launches': 0, 'ms': 0.0, 'work': 0.0, 'bytes': 0.0})
             d['launches'] += 1
             d['ms'] += a.elapsed_time(b)
             d['work'] += work
+            d['bytes'] += nbytes
         return out
 
 
@@ -40,10 +41,11 @@ PROFILE: Optional[KernelProfile] = None
 
 
 class _timed:
-    __slots__ = ('name', 'work', 'a')
+    __slots__ = ('name', 'work', 'nbytes', 'a')
 
-    def __init__(self, name: str, work: float = 0.0):
-        self.name, self.work = name, work
+    def __init__(self, name: str, work: float = 0.0, nbytes: float = 0.0):
+        """work = algorithmic FLOP (jet GEMMs) or bytes (streaming kernels); nbytes = algorithmic HBM bytes of a GEMM"""
+        self.name, self.work, self.nbytes = name, work, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -55,7 +57,7 @@ class _timed:
         if PROFILE is not None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
-            PROFILE.records.append((self.name, self.a, b, self.work))
+            PROFILE.records.append((self.name, self.a, b, self.work, self.nbytes))
         return False
 
 
@@ -153,7 +155,7 @@ def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: 
         out = Jet.empty(zin.cj, zin.rows, n, zin.t.device)
     _lib.launches += 1
     wptr, ldw = _weight_block(w, col_lo, k, n)
-    with _timed(f'jet_fwd_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+    with _timed(f'jet_fwd_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n, 4.0 * zin.cj * zin.rows * (k + n) + 4.0 * k * n):
       check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                   wptr, ldw, _ptr(bias), _ptr(cvec),
                                   cvec.stride(0) if cvec is not None else 0,
@@ -168,7 +170,8 @@ def jet_linear_bwd_dx(gzout: Jet, w: Tensor, col_lo: int, zin: Jet, tin: Optiona
     gzin = Jet.empty(zin.cj, zin.rows, k, zin.t.device)
     _lib.launches += 1
     wptr, ldw = _weight_block(w, col_lo, k, n)
-    with _timed(f'jet_dx_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+    with _timed(f'jet_dx_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n,
+                4.0 * zin.cj * zin.rows * (n + (2 * k if tin is not None else k)) + 4.0 * k * n):
       check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, wptr,
                                      ldw, zin.t.data_ptr(), zin.plane_stride, zin.ld,
                                      C.byref(tin) if tin is not None else None,
@@ -187,7 +190,7 @@ def jet_linear_bwd_dw(gzout: Jet, zin: Jet, tin: Optional[InTrans], gw: Optional
                       workspace: Tensor) -> None:
     lib = _lib.load()
     _lib.launches += 2 + (1 if (gbias is not None or gcvec is not None) else 0)
-    with _timed(f'jet_dw_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n):
+    with _timed(f'jet_dw_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n, 4.0 * zin.cj * zin.rows * (k + n) + 4.0 * k * n):
       check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
                                      zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                      (gw.data_ptr() + 4 * col_lo) if gw is not None else None,

@@ -15,7 +15,11 @@ METRICS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.
            'sm__inst_executed_pipe_tensor.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
            'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
            'launch__shared_mem_per_block_dynamic', 'launch__shared_mem_per_block_static',
-           'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum']
+           'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum',
+           'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+           'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+           'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+           'smsp__issue_active.avg.pct_of_peak_sustained_active']
 
 
 def launches(src, dst, title):
@@ -25,6 +29,8 @@ def launches(src, dst, title):
         try:
             v = float(row['Metric Value'].replace(',', ''))
         except (ValueError, KeyError):
+            continue
+        if v != v:      # a launch cut off by the end of the capture
             continue
         unit = row['Metric Unit']
         v = v / 1e3 if unit == 'ns' else (v * 1e3 if unit == 'ms' else v)
