@@ -47,6 +47,19 @@ SHAPE = dict(n_internal=1500, n_boundary=1000, n_obs=700)
 B_PER_GPU = 32
 N_BATCHES = 4            # distinct synthetic batches cycled through
 
+# BASELINE.json configs 2-5 (config 2 is the default: the one the metric is quoted on for one GPU).  The others are
+# selectable with --config for DESIGN.md's per-config table; their parity is covered by tests/.
+WORKLOADS = {
+    'abc_pipn_pp': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=32,
+                        what='PIPN++ abc 3-D (examples/abc/train.py:36-49)'),
+    'duct_pigano': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=64,
+                        what='PI-GANO duct_variable_boundary 2-D (examples/duct_variable_boundary/train.py:28-37)'),
+    'windbreaks_pigano_pp': dict(shape=dict(n_internal=16384, n_boundary=8192, n_obs=4096), batch=2,
+                                 what='PI-GANO++ windbreaks 3-D (examples/windbreaks/train.py:38-52)'),
+    'manufactured_pipn_pp': dict(shape=dict(n_internal=4096, n_boundary=1024, n_obs=0), batch=32,
+                                 what='PIPN++ manufactured solutions 2-D (examples/manufactured_solutions/train.py:19-27)'),
+}
+
 
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -126,10 +139,11 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': 'PINN train collocation points/sec (fwd+NS-Darcy residual+bwd)',
             'value': pts, 'unit': 'points/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG}: PIPN++ abc 3-D, 1500/1000/700 points, CPU sample of {n_geom} geometries '
-                                   f'per step (bench workload: {B_PER_GPU} per GPU)', 'laplacian': 'reference'},
+            'config': {'workload': f'{CONFIG}: {WORKLOADS[CONFIG]["what"]}, {SHAPE["n_internal"]}/{SHAPE["n_boundary"]}/'
+                                   f'{SHAPE["n_obs"]} points, CPU sample of {n_geom} geometries per step (bench workload: '
+                                   f'{B_PER_GPU} per GPU)', 'laplacian': 'reference'},
             'cpu_baseline': {'value': pts, 'unit': 'points/s', 'cores': threads, 'kind': 'port',
-                             'sample': f'{n_geom} geometries x 1500 collocation points per step, {steps} steps'},
+                             'sample': f'{n_geom} geometries x {SHAPE["n_internal"]} collocation points per step, {steps} steps'},
             'e2e': {'value': pts, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -146,7 +160,21 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--laplacian', default='reference', choices=['reference', 'true'])
+    ap.add_argument('--config', default='abc_pipn_pp', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='geometries per GPU (default: the config\'s own)')
+    ap.add_argument('--n-internal', type=int, default=0,
+                    help='collocation points per geometry (manufactured sweep: boundary = internal / 4)')
     args = ap.parse_args()
+    global CONFIG, SHAPE, B_PER_GPU
+    CONFIG = args.config
+    SHAPE = dict(WORKLOADS[CONFIG]['shape'])
+    B_PER_GPU = args.batch or WORKLOADS[CONFIG]['batch']
+    if args.n_internal:
+        ratio = SHAPE['n_boundary'] / SHAPE['n_internal']
+        obs_ratio = SHAPE['n_obs'] / SHAPE['n_internal']
+        SHAPE = dict(n_internal=args.n_internal, n_boundary=int(args.n_internal * ratio), n_obs=int(args.n_internal * obs_ratio))
+    what = WORKLOADS[CONFIG]['what']
+    shape_txt = f"{SHAPE['n_internal']}/{SHAPE['n_boundary']}/{SHAPE['n_obs']}"
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -346,12 +374,12 @@ def main():
     if not args.no_cpu_baseline:
         pts, ms_cpu, threads = cpu_reference_step_rate(steps=6, warmup=2, n_geom=2)
         cpu = {'value': pts, 'unit': 'points/s', 'cores': threads, 'kind': 'port', 'ms_per_step': ms_cpu,
-               'sample': '2 of the 32 geometries per step (3000 collocation points), 6 timed steps after 2 warm-up'}
+               'sample': f'2 of the {B_PER_GPU} geometries per step ({2 * ni} collocation points), 6 timed steps after 2 warm-up'}
 
     line = {'metric': 'PINN train collocation points/sec (fwd+NS-Darcy residual+bwd)', 'value': value, 'unit': 'points/s',
             'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG}: PIPN++ abc 3-D (examples/abc/train.py:36-49), 1500/1000/700 points, '
+            'config': {'workload': f'{CONFIG}: {what}, {shape_txt} points, '
                                    f'{B_PER_GPU} geometries per GPU', 'global_batch': world * B_PER_GPU,
                        'laplacian': args.laplacian, 'dropout': 'on', 'optimizer': 'fused Adam in the step',
                        'parallelism': f'dp{world}', 'cuda_graph': graph is not None,

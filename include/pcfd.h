@@ -46,7 +46,8 @@ enum { PCFD_ACT_NONE = 0, PCFD_ACT_SILU = 1, PCFD_ACT_TANH = 2 };
 /* ABI version, and the compute capability (major*10+minor) of the current device. */
 int pcfd_abi_version(void);
 int pcfd_device_arch(int* cc_out_host);
-/* Which engine executes the jet GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32. */
+/* Which engine executes the jet GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 with thread-staged operands,
+ * 2 = warp-specialised TMA + tcgen05 3xTF32 (default of the Python host). */
 int pcfd_set_gemm_engine(int engine);
 int pcfd_get_gemm_engine(void);
 
@@ -141,6 +142,12 @@ int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t* arg,
  */
 int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m,
              int64_t* idx_out, void* stream);
+/* Point sets whose coordinates + distances exceed one SM's shared memory (n > ~14k in 3-D) keep their running
+ * min-distances in `workspace` (pcfd_fps_workspace_bytes, 0 for the shared-memory / register paths);
+ * pcfd_fps == pcfd_fps_ws without a workspace and returns PCFD_ERR_WORKSPACE for such sizes. */
+size_t pcfd_fps_workspace_bytes(int32_t n_geom, int32_t n, int32_t dims);
+int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m,
+                int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Ball query, torch_cluster.radius(x=pos, y=pos[idx], r, batch, batch[idx], K) as called at
@@ -224,6 +231,32 @@ int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_rows, int32_
                        const pcfd_residual_params_t* prm_host,
                        float* gy_int, float* gy_bnd, float* out,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* pcfd_residual_loss with DEVICE-resident loss weights (`weights_dev`, one float per loss term; NULL = prm->weights):
+ * the weights of an adaptive scaler change every step without re-recording a captured graph. */
+int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                         const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                         const int64_t* obs_ids, int64_t no,
+                         const float* y_int, int64_t y_plane_stride, const float* y_bnd, int32_t ldy,
+                         const pcfd_residual_params_t* prm_host, const float* weights_dev,
+                         float* gy_int, float* gy_bnd, float* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Residual fields at inference, predict_step with verbose_predict (models/model_base.py:233-252):
+ * fields [n_geom*ni][D+1] = cat([momentum residual (D), divergence]) at the internal points. */
+int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                         const int64_t* internal_ids, int64_t ni,
+                         const float* y_int, int64_t y_plane_stride, int32_t ldy,
+                         const pcfd_residual_params_t* prm_host, float* fields, void* stream);
+
+/* RelobraloScaler.forward (models/losses.py:93-124) on the device: `losses` = the n unscaled loss terms of this
+ * step (out[0..n) of a residual pass), the three buffers are the module's registered buffers, `step` a device
+ * counter (the reference's global_step, incremented here), `batch_size` what the reference reads from
+ * trainer.train_dataloader.batch_size.  Writes the n weights the residual pass applies (all 1 at step 0).
+ * rho ~ Bernoulli(beta) is drawn from a hash of (seed, step). */
+int pcfd_relobralo_update(const float* losses, int32_t n, float* init_losses, float* prev_losses, float* lambda_ema,
+                          int64_t* step, int32_t batch_size, float alpha, float beta, float tau, float eps,
+                          uint64_t seed, float* weights_out, void* stream);
 
 /* out[i] = 0 for i < n (graph-capturable memset of gradient buffers) */
 int pcfd_zero(float* p, int64_t n, void* stream);

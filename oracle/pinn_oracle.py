@@ -284,7 +284,8 @@ def training_step(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
 
     div = continuity_residual(spec, jac)
     cont = (div ** 2).mean()
-    mom = per_component_mean(momentum_residual(spec, internal, labels, u_int, jac, lap, dp) ** 2)
+    mom_field = momentum_residual(spec, internal, labels, u_int, jac, lap, dp)
+    mom = per_component_mean(mom_field ** 2)
 
     terms = [cont, *mom, *bnd_u, bnd_p]
     if spec['enable_data_loss']:
@@ -307,7 +308,9 @@ def training_step(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
     u_err = per_component_mean((u_all - ut).abs())
     p_err = (p_all - pt).abs().mean()
     return {'loss': loss, 'losses': scaled, 'unscaled': unscaled, 'u_error': u_err.detach(),
-            'p_error': p_err.detach(), 'y': y, 'jac': jac, 'lap': lap, 'dp': dp, 'points': pts}
+            'p_error': p_err.detach(), 'y': y, 'jac': jac, 'lap': lap, 'dp': dp, 'points': pts,
+            # predict_step(verbose) residual map (models/model_base.py:250): cat([momentum_error, div])
+            'residuals': torch.cat([mom_field, div.reshape(*mom_field.shape[:-1], 1)], dim=-1).detach()}
 
 
 def step_with_grads(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
@@ -318,3 +321,36 @@ def step_with_grads(spec: dict, p: dict, data: Tensor, labels: dict, domain: dic
     out['loss'].backward()
     out['grads'] = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     return out
+
+
+class Relobralo:
+    """Restatement of RelobraloScaler.forward (reference models/losses.py:93-124) for a fixed Bernoulli draw
+    `rho` (the reference samples torch.bernoulli(beta); beta = 1 -> rho = 1, beta = 0 -> rho = 0).
+    Call once per training step with the unscaled loss vector; returns the weighted vector."""
+
+    def __init__(self, num_losses: int, alpha=0.95, rho=1.0, tau=1.0, eps=1e-8, batch_size=1):
+        self.n, self.alpha, self.rho, self.tau, self.eps, self.batch_size = num_losses, alpha, rho, tau, eps, batch_size
+        self.init = torch.zeros(num_losses)
+        self.prev = torch.zeros(num_losses)
+        self.lam = torch.ones(num_losses)
+        self.step = 0
+
+    def __call__(self, losses: Tensor) -> Tensor:
+        losses = losses.detach().float()
+        step, self.step = self.step, self.step + 1
+        if step == 0:                                             # :99-102
+            self.init, self.prev = losses.clone(), losses.clone()
+            return losses
+        if step % self.batch_size == 0:                           # :106-119
+            self.prev = self.prev / self.batch_size
+            n_prev = (losses / (self.tau * self.prev)).max()
+            n_init = (losses / (self.tau * self.init)).max()
+            l_prev = torch.exp(losses / (self.tau * self.prev + self.eps) - n_prev)
+            l_init = torch.exp(losses / (self.tau * self.init + self.eps) - n_init)
+            l_prev = l_prev * (self.n / (l_prev.sum() + self.eps))
+            l_init = l_init * (self.n / (l_init.sum() + self.eps))
+            self.lam = self.alpha * (self.rho * self.lam + (1.0 - self.rho) * l_init) + (1.0 - self.alpha) * l_prev
+            self.prev = losses.clone()
+        else:                                                     # :126
+            self.prev = self.prev + losses
+        return self.lam * losses                                  # :127

@@ -60,6 +60,8 @@ SIGNATURES = {
     'pcfd_segmax_fwd': (C.c_int, [_P, _I32, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P]),
     'pcfd_segmax_bwd': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _I64, _I32, _I32, _P, _I32, _P]),
     'pcfd_fps': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
+    'pcfd_fps_workspace_bytes': (C.c_size_t, [_I32, _I32, _I32]),
+    'pcfd_fps_ws': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, C.c_size_t, _P]),
     'pcfd_ball_query': (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P, _P]),
     'pcfd_sa_edges': (C.c_int, [_P, _I64, _I32, _I64, _P, _P]),
     'pcfd_sa_gather': (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _I64, _I32, _F, _P, _I32, _P]),
@@ -70,6 +72,10 @@ SIGNATURES = {
     'pcfd_residual_workspace_bytes': (_SZ, [_I32, _I64, _I64, _I64]),
     'pcfd_residual_loss': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
                                      C.POINTER(ResidualParams), _P, _P, _P, _P, _SZ, _P]),
+    'pcfd_residual_loss_w': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
+                                       C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _SZ, _P]),
+    'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
+    'pcfd_relobralo_update': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F, _F, _F, _F, C.c_uint64, _P, _P]),
     'pcfd_zero': (C.c_int, [_P, _I64, _P]),
     'pcfd_advance_seed': (C.c_int, [_P, _P]),
 }

@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ pos
 // in registers, the per-sample arg-max is two redux.sync per warp (max of the distance bits, then min of the
 // indices that attain it -- the same order as the 64-bit key above: largest distance, lowest index) and one
 // barrier across the (few) warps.  ~0.15 us per sample instead of ~0.6 us.
-template <int DIMS, int PPT>
-__global__ void __launch_bounds__(1024) fps_reg_kernel(const float* __restrict__ pos, int n, int m,
+template <int DIMS, int PPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) fps_reg_kernel(const float* __restrict__ pos, int n, int m,
                                                        int64_t* __restrict__ idx_out) {
   extern __shared__ __align__(16) float smem[];
   float* sp = smem;                 // [n][DIMS] (winner lookup)
@@ -114,6 +114,47 @@ __global__ void __launch_bounds__(1024) fps_reg_kernel(const float* __restrict__
     __syncthreads();
     unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
     unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
+    const unsigned gd = __reduce_max_sync(0xffffffffu, vd);
+    cur = (int)__reduce_min_sync(0xffffffffu, vd == gd ? vi : 0xffffffffu);
+    if (tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + cur;
+  }
+}
+
+// Point sets too large for one SM's shared memory (config 5: up to 64k boundary points per geometry): coordinates
+// are read through L1/L2 and the running min-distances live in a caller-provided scratch array [n_geom][n].
+// Same arithmetic and tie rule as above; ~1 us per sample, one CTA of 1024 threads per geometry.
+template <int DIMS>
+__global__ void __launch_bounds__(1024) fps_global_kernel(const float* __restrict__ pos, int n, int m,
+                                                          int64_t* __restrict__ idx_out, float* __restrict__ dist) {
+  __shared__ unsigned slot_d[2][32], slot_i[2][32];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const float* gp = pos + (size_t)g * n * DIMS;
+  float* sd = dist + (size_t)g * n;
+  int cur = 0;
+  if (tid == 0) idx_out[(size_t)g * m] = (int64_t)g * n;
+  for (int s = 1; s < m; ++s) {
+    float c[DIMS];
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) c[d] = __ldg(gp + (size_t)cur * DIMS + d);
+    unsigned bd = 0u, bi = 0xffffffffu;
+    for (int p = tid; p < n; p += nt) {
+      float pp[DIMS];
+#pragma unroll
+      for (int d = 0; d < DIMS; ++d) pp[d] = __ldg(gp + (size_t)p * DIMS + d);
+      float d = sqdist<DIMS>(pp, c);
+      if (s > 1) d = fminf(sd[p], d);
+      sd[p] = d;
+      const unsigned db = __float_as_uint(d);
+      if (db > bd || bi == 0xffffffffu) { bd = db; bi = (unsigned)p; }
+    }
+    const unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    const unsigned wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
+    if (lane == 0) { slot_d[s & 1][warp] = wd; slot_i[s & 1][warp] = wi; }
+    __syncthreads();
+    const unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
+    const unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
     const unsigned gd = __reduce_max_sync(0xffffffffu, vd);
     cur = (int)__reduce_min_sync(0xffffffffu, vd == gd ? vi : 0xffffffffu);
     if (tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + cur;
@@ -238,26 +279,39 @@ __global__ void advance_seed_kernel(uint64_t* seed) { *seed = mix64(*seed); }
 
 using namespace pcfd;
 
-extern "C" int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
-                        void* stream) {
+extern "C" size_t pcfd_fps_workspace_bytes(int32_t n_geom, int32_t n, int32_t dims) {
+  if (n_geom <= 0 || n <= 0) return 0;
+  return (size_t)n * (dims + 1) * sizeof(float) > 220 * 1024 ? (size_t)n_geom * n * sizeof(float) : 0;
+}
+
+extern "C" int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   if (!pos || !idx_out || n_geom <= 0 || n <= 0 || m <= 0 || m > n || (dims != 2 && dims != 3)) return PCFD_ERR_ARG;
   const size_t smem = (size_t)n * (dims + 1) * sizeof(float);
-  if (smem > 220 * 1024) return PCFD_ERR_ARG;   // larger point sets need the clustered variant (not built yet)
+  if (smem > 220 * 1024) {
+    if (workspace == nullptr || workspace_bytes < pcfd_fps_workspace_bytes(n_geom, n, dims)) return PCFD_ERR_WORKSPACE;
+    if (dims == 2) fps_global_kernel<2><<<n_geom, 1024, 0, (cudaStream_t)stream>>>(pos, n, m, idx_out, (float*)workspace);
+    else fps_global_kernel<3><<<n_geom, 1024, 0, (cudaStream_t)stream>>>(pos, n, m, idx_out, (float*)workspace);
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (n <= 8192) {
+    // 8 or 16 points per thread (measured: 32 per thread is slower at n = 8192)
     const size_t rsmem = (size_t)n * dims * sizeof(float);
-    const int ppt = 8;
+    const int ppt = n <= 1024 ? 8 : (n <= 4096 ? 16 : 8);
     int rthreads = (n + ppt - 1) / ppt;
     rthreads = (rthreads + 31) / 32 * 32;
     if (rthreads < 32) rthreads = 32;
-#define PCFD_FPS_REG(D_, P_)                                                                                        \
-    {                                                                                                               \
-      e = cudaFuncSetAttribute(fps_reg_kernel<D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);    \
-      if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;                                                          \
-      fps_reg_kernel<D_, P_><<<n_geom, rthreads, rsmem, st>>>(pos, n, m, idx_out);                                  \
+#define PCFD_FPS_REG(D_, P_)                                                                                             \
+    {                                                                                                                    \
+      e = cudaFuncSetAttribute(fps_reg_kernel<D_, P_, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);   \
+      if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;                                                               \
+      fps_reg_kernel<D_, P_, 1024><<<n_geom, rthreads, rsmem, st>>>(pos, n, m, idx_out);                                 \
     }
-    if (dims == 2) PCFD_FPS_REG(2, 8) else PCFD_FPS_REG(3, 8)
+    if (dims == 2) { if (ppt == 8) PCFD_FPS_REG(2, 8) else PCFD_FPS_REG(2, 16) }
+    else { if (ppt == 8) PCFD_FPS_REG(3, 8) else PCFD_FPS_REG(3, 16) }
 #undef PCFD_FPS_REG
     PCFD_CHECK_LAUNCH();
     return PCFD_OK;
@@ -274,6 +328,11 @@ extern "C" int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dim
   }
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
+}
+
+extern "C" int pcfd_fps(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
+                        void* stream) {
+  return pcfd_fps_ws(pos, n_geom, n, dims, m, idx_out, nullptr, 0, stream);
 }
 
 extern "C" int pcfd_ball_query(const float* pos, const int64_t* centroid_idx, int32_t n_geom, int32_t n, int32_t dims,

@@ -23,7 +23,11 @@ struct ResArgs {
   float inv_int, inv_bnd, inv_obs;   // 1 / (n_geom * count)
   int n_geom;
   float* partial;                     // this kernel's [blocks][NSLOT]
+  const float* wdev;                  // optional device-resident loss weights (ReLoBRaLo); else p.weights
+  float* fields;                      // optional per-point residual map [n_geom*ni][D+1] = (momentum xD, div)
 };
+
+#define PCFD_WT(i) (a.wdev != nullptr ? __ldg(a.wdev + (i)) : P.weights[i])
 
 __device__ __forceinline__ void block_reduce_store(float (&v)[NSLOT], float* partial) {
   __shared__ float red[8][NSLOT];
@@ -118,6 +122,11 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
     sums[0] = div * div;
 #pragma unroll
     for (int c = 0; c < D; ++c) sums[1 + c] = res[c] * res[c];
+    if (a.fields != nullptr) {          // predict_step(verbose): residuals = cat([momentum_error, div]) (models/model_base.py:250)
+#pragma unroll
+      for (int c = 0; c < D; ++c) a.fields[t * (D + 1) + c] = res[c];
+      a.fields[t * (D + 1) + D] = div;
+    }
     // MAE log values on de-standardised fields
 #pragma unroll
     for (int d = 0; d < D; ++d) sums[1 + D + d] = fabsf(su[d] * (y[0][d] - __ldg(erow + P.col_u[d])));
@@ -129,10 +138,10 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
     for (int c = 0; c < CJ; ++c)
 #pragma unroll
       for (int o = 0; o <= D; ++o) gy[c][o] = 0.0f;
-    const float gdiv = 2.0f * P.weights[0] * div * a.inv_int;
+    const float gdiv = 2.0f * PCFD_WT(0) * div * a.inv_int;
     float gr[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) gr[c] = 2.0f * P.weights[1 + c] * res[c] * a.inv_int;
+    for (int c = 0; c < D; ++c) gr[c] = 2.0f * PCFD_WT(1 + c) * res[c] * a.inv_int;
 #pragma unroll
     for (int d = 0; d < D; ++d) gy[1 + d][d] += gdiv * su[d] / sx[d];
     float gur[D];   // gradient wrt u_raw
@@ -165,12 +174,14 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) gy[0][d] += gur[d] * su[d];
+    if (a.gy_int != nullptr) {
 #pragma unroll
-    for (int c = 0; c < CJ; ++c)
+      for (int c = 0; c < CJ; ++c)
 #pragma unroll
-      for (int o = 0; o <= D; ++o) a.gy_int[c * a.ps + t * a.ldy + o] = gy[c][o];
+        for (int o = 0; o <= D; ++o) a.gy_int[c * a.ps + t * a.ldy + o] = gy[c][o];
+    }
   }
-  block_reduce_store(sums, a.partial);
+  if (a.partial != nullptr) block_reduce_store(sums, a.partial);
 }
 
 // slots: [0..D-1] (U - target)^2, [D] (p - target)^2, [D+1..2D] |U error|, [2D+1] |p error|
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(256) residual_boundary_kernel(ResArgs a) {
       const int col = o < D ? P.col_u[o] : P.col_p;
       const float diff = yv - __ldg(drow + col);
       sums[o] = diff * diff;
-      const float w = P.weights[1 + D + o];
+      const float w = PCFD_WT(1 + D + o);
       a.gy_bnd[t * a.ldy + o] = 2.0f * w * diff * a.inv_bnd;
       const float sc = manu ? 1.0f : (o < D ? P.u_std[o] : P.p_std);
       sums[D + 1 + o] = fabsf(sc * (yv - __ldg(erow + col)));
@@ -223,7 +234,7 @@ __global__ void __launch_bounds__(256) residual_obs_kernel(ResArgs a) {
       const int col = o < D ? P.col_u[o] : P.col_p;
       const float diff = __ldg(yrow + o) - __ldg(drow + col);
       sums[o] = diff * diff;
-      atomicAdd(grow + o, 2.0f * P.weights[2 + 2 * D + o] * diff * a.inv_obs);
+      atomicAdd(grow + o, 2.0f * PCFD_WT(2 + 2 * D + o) * diff * a.inv_obs);
     }
   }
   block_reduce_store(sums, a.partial);
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(256) residual_obs_kernel(ResArgs a) {
 
 struct FinishArgs {
   const float* p_int; int b_int; const float* p_bnd; int b_bnd; const float* p_obs; int b_obs;
-  int dims, data_loss; float inv_int, inv_bnd, inv_obs, inv_all; float weights[16]; float* out;
+  int dims, data_loss; float inv_int, inv_bnd, inv_obs, inv_all; float weights[16]; const float* wdev; float* out;
 };
 
 __global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
     if (a.data_loss)
       for (int c = 0; c <= D; ++c) out[n++] = (float)(tot[2 * NSLOT + c] * a.inv_obs);
     float total = 0.0f;
-    for (int i = 0; i < n; ++i) { out[16 + i] = out[i] * a.weights[i]; total += out[16 + i]; }
+    for (int i = 0; i < n; ++i) { out[16 + i] = out[i] * (a.wdev != nullptr ? a.wdev[i] : a.weights[i]); total += out[16 + i]; }
     out[32] = total;
     for (int c = 0; c < D; ++c) out[33 + c] = (float)((tot[1 + D + c] + tot[NSLOT + D + 1 + c]) * a.inv_all);
     out[36] = (float)((tot[1 + 2 * D] + tot[NSLOT + 2 * D + 1]) * a.inv_all);
@@ -283,12 +294,12 @@ extern "C" size_t pcfd_residual_workspace_bytes(int32_t n_geom, int64_t ni, int6
   return blocks * NSLOT * sizeof(float);
 }
 
-extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
-                                  const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
-                                  const int64_t* obs_ids, int64_t no, const float* y_int, int64_t y_plane_stride,
-                                  const float* y_bnd, int32_t ldy, const pcfd_residual_params_t* prm,
-                                  float* gy_int, float* gy_bnd, float* out, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+extern "C" int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                                    const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                                    const int64_t* obs_ids, int64_t no, const float* y_int, int64_t y_plane_stride,
+                                    const float* y_bnd, int32_t ldy, const pcfd_residual_params_t* prm,
+                                    const float* weights_dev, float* gy_int, float* gy_bnd, float* out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
   if (!data || !internal_ids || !boundary_ids || !y_int || !y_bnd || !prm || !gy_int || !gy_bnd || !out || !workspace)
     return PCFD_ERR_ARG;
   if (n_geom <= 0 || ni <= 0 || nb <= 0 || (prm->dims != 2 && prm->dims != 3) || ldy < prm->dims + 1) return PCFD_ERR_ARG;
@@ -300,7 +311,7 @@ extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_r
   a.data = data; a.n_rows = n_rows; a.f = f;
   a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = boundary_ids; a.nb = nb; a.obs_ids = obs_ids; a.no = no;
   a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = y_bnd; a.ldy = ldy; a.gy_int = gy_int; a.gy_bnd = gy_bnd;
-  a.p = *prm; a.n_geom = n_geom;
+  a.p = *prm; a.n_geom = n_geom; a.wdev = weights_dev; a.fields = nullptr;
   a.inv_int = 1.0f / (float)((double)n_geom * ni);
   a.inv_bnd = 1.0f / (float)((double)n_geom * nb);
   a.inv_obs = no > 0 ? 1.0f / (float)((double)n_geom * no) : 0.0f;
@@ -332,8 +343,96 @@ extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_r
   fa.inv_int = a.inv_int; fa.inv_bnd = a.inv_bnd; fa.inv_obs = a.inv_obs;
   fa.inv_all = 1.0f / (float)((double)n_geom * (ni + nb));
   for (int i = 0; i < 16; ++i) fa.weights[i] = prm->weights[i];
+  fa.wdev = weights_dev;
   fa.out = out;
   residual_finish_kernel<<<1, 256, 0, st>>>(fa);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                                  const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                                  const int64_t* obs_ids, int64_t no, const float* y_int, int64_t y_plane_stride,
+                                  const float* y_bnd, int32_t ldy, const pcfd_residual_params_t* prm,
+                                  float* gy_int, float* gy_bnd, float* out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  return pcfd_residual_loss_w(data, n_geom, n_rows, f, internal_ids, ni, boundary_ids, nb, obs_ids, no, y_int,
+                              y_plane_stride, y_bnd, ldy, prm, nullptr, gy_int, gy_bnd, out, workspace, workspace_bytes,
+                              stream);
+}
+
+// Per-point residual map of the internal points (predict_step with verbose_predict, models/model_base.py:233-252):
+// fields [n_geom*ni][D+1] = (momentum residual x D, divergence).
+extern "C" int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                                    const int64_t* internal_ids, int64_t ni, const float* y_int, int64_t y_plane_stride,
+                                    int32_t ldy, const pcfd_residual_params_t* prm, float* fields, void* stream) {
+  if (!data || !internal_ids || !y_int || !prm || !fields) return PCFD_ERR_ARG;
+  if (n_geom <= 0 || ni <= 0 || (prm->dims != 2 && prm->dims != 3) || ldy < prm->dims + 1) return PCFD_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  ResArgs a;
+  a.data = data; a.n_rows = n_rows; a.f = f;
+  a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = nullptr; a.nb = 0; a.obs_ids = nullptr; a.no = 0;
+  a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = nullptr; a.ldy = ldy; a.gy_int = nullptr; a.gy_bnd = nullptr;
+  a.p = *prm; a.n_geom = n_geom; a.wdev = nullptr; a.fields = fields; a.partial = nullptr;
+  a.inv_int = 1.0f / (float)((double)n_geom * ni); a.inv_bnd = 0.0f; a.inv_obs = 0.0f;
+  const int b_int = blocks_for((int64_t)n_geom * ni);
+  const int D = prm->dims;
+  if (D == 2 && prm->lap_mode == PCFD_LAP_REFERENCE) residual_internal_kernel<2, PCFD_LAP_REFERENCE><<<b_int, 256, 0, st>>>(a);
+  else if (D == 2) residual_internal_kernel<2, PCFD_LAP_TRUE><<<b_int, 256, 0, st>>>(a);
+  else if (prm->lap_mode == PCFD_LAP_REFERENCE) residual_internal_kernel<3, PCFD_LAP_REFERENCE><<<b_int, 256, 0, st>>>(a);
+  else residual_internal_kernel<3, PCFD_LAP_TRUE><<<b_int, 256, 0, st>>>(a);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+// ReLoBRaLo loss balancing on the device (models/losses.py:64-124), one thread: reads the unscaled loss terms of the
+// current step and the module's buffers, writes the weights the residual pass applies.  `step` counts calls (the
+// reference's global_step); rho ~ Bernoulli(beta) comes from a counter-based hash of (seed, step) instead of
+// torch.bernoulli's global generator.
+__global__ void relobralo_kernel(const float* __restrict__ losses, int n, float* init_l, float* prev_l, float* lam,
+                                 int64_t* step, int batch_size, float alpha, float beta, float tau, float eps,
+                                 uint64_t seed, float* weights) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int64_t s = *step;
+  if (s == 0) {
+    for (int i = 0; i < n; ++i) { init_l[i] = losses[i]; prev_l[i] = losses[i]; weights[i] = 1.0f; }
+  } else {
+    if (s % batch_size == 0) {
+      float np = -INFINITY, ni = -INFINITY;
+      for (int i = 0; i < n; ++i) {
+        prev_l[i] = prev_l[i] / (float)batch_size;
+        np = fmaxf(np, losses[i] / (tau * prev_l[i]));
+        ni = fmaxf(ni, losses[i] / (tau * init_l[i]));
+      }
+      const float u = (float)(mix64(seed ^ (uint64_t)s * 0x9e3779b97f4a7c15ULL) >> 40) * (1.0f / 16777216.0f);
+      const float rho = u < beta ? 1.0f : 0.0f;
+      float lp[16], li[16], sp = 0.0f, si = 0.0f;
+      for (int i = 0; i < n; ++i) {
+        lp[i] = expf(losses[i] / (tau * prev_l[i] + eps) - np);
+        li[i] = expf(losses[i] / (tau * init_l[i] + eps) - ni);
+        sp += lp[i]; si += li[i];
+      }
+      for (int i = 0; i < n; ++i) {
+        lp[i] *= (float)n / (sp + eps);
+        li[i] *= (float)n / (si + eps);
+        lam[i] = alpha * (rho * lam[i] + (1.0f - rho) * li[i]) + (1.0f - alpha) * lp[i];
+        prev_l[i] = losses[i];
+      }
+    } else {
+      for (int i = 0; i < n; ++i) prev_l[i] += losses[i];
+    }
+    for (int i = 0; i < n; ++i) weights[i] = lam[i];
+  }
+  *step = s + 1;
+}
+
+extern "C" int pcfd_relobralo_update(const float* losses, int32_t n, float* init_losses, float* prev_losses,
+                                     float* lambda_ema, int64_t* step, int32_t batch_size, float alpha, float beta,
+                                     float tau, float eps, uint64_t seed, float* weights_out, void* stream) {
+  if (!losses || !init_losses || !prev_losses || !lambda_ema || !step || !weights_out || n <= 0 || n > 16 || batch_size <= 0)
+    return PCFD_ERR_ARG;
+  relobralo_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(losses, n, init_losses, prev_losses, lambda_ema, step, batch_size, alpha,
+                                                       beta, tau, eps, seed, weights_out);
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
 }

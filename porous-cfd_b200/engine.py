@@ -395,6 +395,30 @@ class PinnExecutor:
         ops.end_step()
         return zs[-1].values().reshape(b, n, d + 1)
 
+    def predict_with_residuals(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference'):
+        """predict_step(verbose): predictions at all points (B, N, D+1) and the residual map of the internal
+        points (B, NI, D+1) = cat([momentum residual, divergence]) (reference models/model_base.py:233-252).
+        One jet forward, no reduction, no backward."""
+        plan, ctx, model = self.plan, self.ctx, self.model
+        ctx.training = model.training
+        b, n_rows, f = data.shape
+        d = plan['dims']
+        int_ids, bnd_ids = domain['internal'], domain['boundary']
+        ni, nb = int_ids.shape[1], bnd_ids.shape[1]
+        cj = 1 + d if laplacian == 'reference' else 1 + 2 * d
+        c_cols = self._cols(labels, 'C')
+        ops.begin_step()
+        cvecs, escale, _ = self._encode(data, labels, domain, int_ids, bnd_ids, None)
+        z0_int = ops.seed_jet(data, int_ids, ni, c_cols, cj)
+        z0_bnd = ops.seed_jet(data, bnd_ids, nb, c_cols, 1)
+        layers = plan['point_layers']
+        y_int = chain_forward(ctx, layers, z0_int, ni, escale, cvecs, salt_base=100)[-1]
+        y_bnd = chain_forward(ctx, layers, z0_bnd, nb, escale, cvecs, salt_base=200)[-1]
+        ops.end_step()
+        fields = ops.residual_fields(data, int_ids, y_int, model.residual_params(labels, laplacian))
+        pred = torch.cat([y_int.values().reshape(b, ni, d + 1), y_bnd.values().reshape(b, nb, d + 1)], dim=1)
+        return pred, fields
+
     def step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
              keep_outputs: bool = False) -> StepResult:
         """One fused training step: fills the flat gradient buffer and returns the loss vector."""
@@ -427,8 +451,19 @@ class PinnExecutor:
 
         prm = model.residual_params(labels, laplacian)
         ctx.need_workspace(ops.residual_workspace_bytes(b, ni, nb, obs_ids.shape[1] if obs_ids is not None else 0))
+        scaler = getattr(model, 'loss_scaler', None)
+        weights_dev = None
+        if scaler is not None and getattr(scaler, 'dynamic', False) and ctx.training:
+            # adaptive weights (ReLoBRaLo): unscaled terms first, buffer / weight update on the device, then the weighted
+            # pass with the device-resident weights (models/losses.py:93-124)
+            n_terms = 2 * d + 2 + ((d + 1) if obs_ids is not None else 0)
+            _, _, out0 = ops.residual_loss(data, int_ids, bnd_ids, obs_ids, zs_int[-1], zs_bnd[-1], prm, ctx.workspace)
+            step_dev, weights_dev = scaler.device_state(data.device)
+            ops.relobralo_update(out0, n_terms, scaler.init_losses, scaler.prev_losses, scaler.lambda_ema, step_dev,
+                                 scaler.batch_size, scaler.alpha, scaler.beta, scaler.tau, scaler.eps, scaler.seed,
+                                 weights_dev)
         gy_int, gy_bnd, out = ops.residual_loss(data, int_ids, bnd_ids, obs_ids, zs_int[-1], zs_bnd[-1], prm,
-                                                ctx.workspace)
+                                                ctx.workspace, weights_dev)
 
         gcvecs = {'concat': torch.empty_like(cvecs['concat'])}
         ops.zero_(gcvecs['concat'])

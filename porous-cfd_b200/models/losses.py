@@ -49,9 +49,18 @@ class FixedLossScaler(LossScaler):
 
 
 class RelobraloScaler(LossScaler):
-    """ReLoBRaLo buffers (reference models/losses.py:64-124) are kept so checkpoints load; the
-    adaptive update itself is listed as a 'next' row and is not
-    implemented on the device path yet."""
+    """ReLoBRaLo adaptive weighting (reference models/losses.py:64-124), same constructor, same registered
+    buffers (`init_losses`, `prev_losses`, `lambda_ema`: reference checkpoints load with strict=True).
+
+    The update runs on the device inside the fused step (`pcfd_relobralo_update`, csrc/residual.cu): the step
+    evaluates the unscaled loss terms, updates the buffers and the weight vector in one single-thread kernel,
+    then evaluates the weighted loss and its gradient with the device-resident weights -- no host read, so the
+    whole step stays graph-capturable.  `global_step` is a device counter advanced by the kernel;
+    `batch_size` is what the reference reads from `model.trainer.train_dataloader.batch_size` (set it with
+    `set_batch_size`, default 1).  rho ~ Bernoulli(beta) comes from a counter-based hash of (seed, step), not from
+    torch's global generator: identical in distribution, bit-identical to the reference only for beta in {0, 1}.
+    """
+    dynamic = True
 
     def __init__(self, num_losses: int, alpha=0.95, beta=0.99, tau=1.0, eps=1e-8):
         super().__init__()
@@ -59,9 +68,30 @@ class RelobraloScaler(LossScaler):
         self.register_buffer('init_losses', torch.zeros(num_losses))
         self.register_buffer('prev_losses', torch.zeros(num_losses))
         self.register_buffer('lambda_ema', torch.ones(num_losses))
+        self.batch_size = 1
+        self.seed = 8421
+        self._step = None       # device int64 counter
+        self._weights = None    # device float32[16]
+
+    def set_batch_size(self, batch_size: int) -> None:
+        self.batch_size = int(batch_size)
 
     def weights(self, n_terms: int) -> list[float]:
-        raise NotImplementedError('RelobraloScaler is not available on the CUDA path yet; use FixedLossScaler')
+        return [1.0] * n_terms     # the static slot of the residual parameters; the live weights are on the device
+
+    def device_state(self, device):
+        if self._step is None or self._step.device != device:
+            self._step = torch.zeros(1, dtype=torch.int64, device=device)
+            self._weights = torch.ones(16, dtype=torch.float32, device=device)
+        return self._step, self._weights
+
+    def forward(self, model, losses: Tensor) -> Tensor:
+        """Host-callable form (the fused step does not go through here): weights `losses` with the current state."""
+        from .. import ops
+        step, w = self.device_state(losses.device)
+        ops.relobralo_update(losses.detach().contiguous(), self.num_losses, self.init_losses, self.prev_losses,
+                             self.lambda_ema, step, self.batch_size, self.alpha, self.beta, self.tau, self.eps, self.seed, w)
+        return w[:self.num_losses] * losses
 
 
 class LossLogger:
@@ -88,8 +118,8 @@ class _ResidualSpec(nn.Module):
         self.u_scaler = self.points_scaler = self.p_scaler = self.d_scaler = self.f_scaler = None
 
     def func(self, *args):
-        raise NotImplementedError('per-point residual fields (predict_step verbose path) are a "next" row '
-                                  '(SURVEY.md section 8f rank 3); the training step uses the fused reduction')
+        raise NotImplementedError('per-point residual fields come from PorousPinnBase.predict_step with '
+                                  'verbose_predict=True (pcfd_residual_fields); the loss modules hold constants only')
 
     def forward(self, *args):
         raise NotImplementedError('losses are evaluated inside PorousPinnBase.training_step by pcfd_residual_loss')

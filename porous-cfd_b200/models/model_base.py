@@ -200,7 +200,11 @@ class PorousPinnBase(_Base):
 
     def predict_step(self, batch: FoamData, batch_idx: int = 0):
         if self.verbose_predict:
-            raise NotImplementedError('residual fields at inference are a "next" row (SURVEY.md section 8f rank 3)')
+            # (predicted, residuals): residuals = cat([momentum_error, div]) on the internal points
+            # (reference models/model_base.py:233-252), from one jet forward + pcfd_residual_fields
+            pred, fields = self.executor.predict_with_residuals(batch.data, batch.labels, batch.domain, self.laplacian)
+            return (FoamData(pred, self.predicted_labels, batch.domain),
+                    FoamData(fields, self.extra_labels, batch.domain))
         return self.forward(batch['C'], batch)
 
     def jets(self, batch: FoamData, laplacian: str = 'true') -> dict:

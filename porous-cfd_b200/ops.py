@@ -230,8 +230,10 @@ def fps(pos: Tensor, ratio: float) -> Tensor:
     m = int(math.ceil(ratio * n))
     idx = torch.empty((b, m), dtype=torch.int64, device=pos.device)
     _lib.launches += 1
+    need = int(lib.pcfd_fps_workspace_bytes(b, n, d))
+    ws = torch.empty(need, dtype=torch.uint8, device=pos.device) if need else None
     with _timed('fps', 4.0 * b * n * d + 8.0 * b * m):
-      check(lib.pcfd_fps(pos.data_ptr(), b, n, d, m, idx.data_ptr(), _stream()), 'pcfd_fps')
+      check(lib.pcfd_fps_ws(pos.data_ptr(), b, n, d, m, idx.data_ptr(), _ptr(ws), need, _stream()), 'pcfd_fps_ws')
     return idx
 
 
@@ -309,8 +311,9 @@ def residual_workspace_bytes(n_geom: int, ni: int, nb: int, no: int) -> int:
 
 
 def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_ids: Optional[Tensor],
-                  y_int: Jet, y_bnd: Jet, prm: ResidualParams, workspace: Tensor):
-    """-> (gy_int Jet, gy_bnd Jet, out float32[48])"""
+                  y_int: Jet, y_bnd: Jet, prm: ResidualParams, workspace: Tensor, weights_dev: Optional[Tensor] = None):
+    """-> (gy_int Jet, gy_bnd Jet, out float32[48]).  `weights_dev`: device-resident loss weights (adaptive
+    scaler) instead of prm.weights."""
     lib = _lib.load()
     b, n_rows, f = data.shape
     ni, nb = internal_ids.shape[1], boundary_ids.shape[1]
@@ -320,12 +323,36 @@ def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_
     out = torch.empty(_lib.LOSS_OUT_FLOATS, dtype=torch.float32, device=data.device)
     _lib.launches += 4
     with _timed('residual_loss', 8.0 * b * ni * y_int.cj * y_int.ld + 4.0 * b * ni * f + 8.0 * b * nb * y_int.ld):
-      check(lib.pcfd_residual_loss(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
-                                 nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
-                                 y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), gy_int.t.data_ptr(), gy_bnd.t.data_ptr(),
-                                 out.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-                                 _stream()), 'pcfd_residual_loss')
+      check(lib.pcfd_residual_loss_w(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
+                                   nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
+                                   y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), _ptr(weights_dev), gy_int.t.data_ptr(),
+                                   gy_bnd.t.data_ptr(), out.data_ptr(), workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(), _stream()), 'pcfd_residual_loss_w')
     return gy_int, gy_bnd, out
+
+
+def residual_fields(data: Tensor, internal_ids: Tensor, y_int: Jet, prm: ResidualParams) -> Tensor:
+    """-> (B, NI, D+1) = cat([momentum residual, divergence]) at the internal points (predict_step, verbose)."""
+    lib = _lib.load()
+    b, n_rows, f = data.shape
+    ni = internal_ids.shape[1]
+    d = prm.dims
+    out = torch.empty((b, ni, d + 1), dtype=torch.float32, device=data.device)
+    _lib.launches += 1
+    check(lib.pcfd_residual_fields(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, y_int.t.data_ptr(),
+                                   y_int.plane_stride, y_int.ld, C.byref(prm), out.data_ptr(), _stream()),
+          'pcfd_residual_fields')
+    return out
+
+
+def relobralo_update(losses: Tensor, n: int, init_losses: Tensor, prev_losses: Tensor, lambda_ema: Tensor, step: Tensor,
+                     batch_size: int, alpha: float, beta: float, tau: float, eps: float, seed: int,
+                     weights_out: Tensor) -> None:
+    lib = _lib.load()
+    _lib.launches += 1
+    check(lib.pcfd_relobralo_update(losses.data_ptr(), n, init_losses.data_ptr(), prev_losses.data_ptr(),
+                                    lambda_ema.data_ptr(), step.data_ptr(), batch_size, alpha, beta, tau, eps, seed,
+                                    weights_out.data_ptr(), _stream()), 'pcfd_relobralo_update')
 
 
 def zero_(t: Tensor) -> None:

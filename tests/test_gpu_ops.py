@@ -47,7 +47,7 @@ def test_fps_and_ball_query_match_fixture_bit_exact(ops, tag):
 
 
 @pytest.mark.parametrize('shape', [(4, 1000, 3, 0.5), (3, 777, 2, 0.25), (2, 4096, 3, 0.25), (1, 8192, 3, 0.5),
-                                   (5, 33, 3, 0.5), (2, 1, 3, 1.0)])
+                                   (5, 33, 3, 0.5), (2, 1, 3, 1.0), (2, 20000, 3, 0.02), (1, 30000, 2, 0.01)])
 def test_fps_bit_exact_against_oracle(ops, shape):
     nb, n, d, ratio = shape
     g = torch.Generator().manual_seed(n)
@@ -64,6 +64,11 @@ def test_fps_bit_exact_against_oracle(ops, shape):
 def test_fps_ties_pick_lowest_index(ops):
     pos = torch.tensor([[[0., 0.], [1., 0.], [1., 0.], [0., 1.], [0., 1.], [0.5, 0.5]]])
     assert ops.fps(dev(pos), 0.5).cpu().flatten().tolist() == [0, 1, 3]
+    # more samples than distinct points: zero-distance ties still resolve to the lowest unused... index 0 repeats
+    pos = torch.zeros(1, 40, 3)
+    pos[0, 20:] = 1.0
+    want = pyg_restate.fps(pos.reshape(-1, 3), torch.zeros(40, dtype=torch.long), 0.25)
+    assert torch.equal(ops.fps(dev(pos), 0.25).cpu().flatten(), want)
 
 
 @pytest.mark.parametrize('shape', [(3, 500, 3, 0.5, 0.5, 16), (2, 1000, 2, 0.25, 0.3, 64), (2, 300, 3, 0.5, 3.0, 8)])
@@ -268,3 +273,22 @@ def test_dropout_mask_is_consistent_between_passes(ops):
     ops.advance_seed(seed)
     out2 = ops.jet_linear_fwd(zj, tin, w, 0, k, None, None, 0, n).t[0, :, :n]
     assert not torch.equal(out2 != 0, kept)
+
+
+# ---------------------------------------------------------------------------------------------
+# ReLoBRaLo update kernel against the vectors of the reference's RelobraloScaler
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['rho1_b1', 'rho0_b3', 'rho1_b2_tau'])
+def test_relobralo_kernel_matches_reference_vectors(ops, case):
+    z = np.load(f'{GOLDEN}/relobralo.npz')
+    n, alpha, beta, tau, bs, steps = z[f'{case}/meta']
+    n, bs, steps = int(n), int(bs), int(steps)
+    init, prev, lam = (torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda'), torch.ones(n, device='cuda'))
+    step = torch.zeros(1, dtype=torch.int64, device='cuda')
+    w = torch.ones(16, device='cuda')
+    for s in range(steps):
+        losses = dev(torch.from_numpy(z[f'{case}/losses'][s]))
+        ops.relobralo_update(losses, n, init, prev, lam, step, bs, float(alpha), float(beta), float(tau), 1e-8, 8421, w)
+        got = (w[:n] * losses).cpu()
+        assert max_rel(got, torch.from_numpy(z[f'{case}/weighted'][s])) < 1e-5, (case, s)
+    assert int(step.item()) == steps

@@ -182,3 +182,52 @@ def test_gradient_is_linear_in_loss_weights():
     keys = [k for k, _ in m1.named_parameters()]
     assert rel_l2(flat(g2, keys), 2 * flat(g1, keys)) < 1e-5
     assert max_rel(r2.losses, 2 * r1.losses) < 1e-6
+
+
+@pytest.mark.parametrize('name', PER_POINT)
+@pytest.mark.parametrize('mode', ['reference', 'true'])
+def test_predict_step_returns_residual_fields(name, mode):
+    """predict_step with verbose_predict (models/model_base.py:233-252): (predicted, residuals) with
+    residuals = cat([momentum_error, div]) on the internal points."""
+    spec = synthetic.model_spec(name)
+    data, domain, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    model.verbose_predict, model.laplacian = True, mode
+    pred, res = model.predict_step(FoamData(data, labels, domain).to('cuda'))
+    orc = pinn_oracle.training_step(spec, params, data, labels, domain, mode)
+    d = spec['dims']
+    assert res.data.shape == (data.shape[0], domain['internal'].shape[1], d + 1)
+    assert rel_l2(pred.data.cpu().double(), orc['y'].detach().double()) < 1e-5
+    assert rel_l2(res.data.cpu().double(), orc['residuals'].double()) < TOL
+    assert rel_l2(res['div'].cpu().double().flatten(), orc['residuals'][..., d].double().flatten()) < TOL
+
+
+def test_training_step_with_relobralo_scaler():
+    """The fused step with the adaptive scaler: per-step weighted losses equal the reference scaler's
+    (oracle.Relobralo, pinned on the reference's vectors) applied to the step's unscaled losses, buffers keep the
+    reference's state_dict names, and the gradient is the weighted combination."""
+    from porous_cfd_b200.models.losses import RelobraloScaler
+    spec = synthetic.model_spec('tiny_pipn_pp')
+    data, domain, params, _ = load_fixture('tiny_pipn_pp')
+    labels = synthetic.build_labels(spec['layout'])
+    model = factory.build_model(spec)
+    model.load_state_dict(params, strict=True)
+    n = 12
+    model.loss_scaler = RelobraloScaler(n, alpha=0.9, beta=1.0)
+    model.loss_scaler.set_batch_size(2)
+    assert {'loss_scaler.init_losses', 'loss_scaler.prev_losses', 'loss_scaler.lambda_ema'} <= set(model.state_dict())
+    model = model.to('cuda').train()
+    batch = FoamData(data, labels, domain).to('cuda')
+    restated = pinn_oracle.Relobralo(n, alpha=0.9, rho=1.0, batch_size=2)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-12)   # the loss terms vary from step to step through dropout
+    for step in range(5):
+        res = model.fused_step(batch, 'reference')
+        want = restated(res.unscaled.cpu())
+        assert max_rel(res.losses, want) < 1e-4, step
+        assert abs(float(res.loss) - float(want.sum())) / float(want.sum()) < 1e-4
+        loss = model.training_step(batch, step)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        restated(model.last_step.unscaled.cpu())

@@ -100,3 +100,15 @@ def test_oracle_matches_live_reference():
     loss, losses, _, _, grads = mg.reference_step(model, spec, data, labels, domain, 'reference')
     got = pinn_oracle.step_with_grads(spec, params, data, labels, domain, 'reference')
     assert max_rel(got['losses'], losses) < TOL
+
+
+@pytest.mark.parametrize('case', ['rho1_b1', 'rho0_b3', 'rho1_b2_tau'])
+def test_relobralo_restatement_matches_reference_vectors(case):
+    """oracle.Relobralo against the weighted loss vectors the reference's RelobraloScaler returned
+    (tests/golden/relobralo.npz, written by tests/golden/make_relobralo_golden.py)."""
+    z = np.load(f'{GOLDEN}/relobralo.npz')
+    n, alpha, beta, tau, bs, steps = z[f'{case}/meta']
+    sc = pinn_oracle.Relobralo(int(n), alpha=float(alpha), rho=float(beta), tau=float(tau), batch_size=int(bs))
+    for s in range(int(steps)):
+        got = sc(torch.from_numpy(z[f'{case}/losses'][s]))
+        assert max_rel(got, torch.from_numpy(z[f'{case}/weighted'][s])) < 1e-6
