@@ -13,7 +13,7 @@ int pcfd_ffma_jet_linear_bwd_dw(const float*, int64_t, int32_t, const float*, in
                                 void*, size_t, void*);
 size_t pcfd_ffma_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
 int pcfd_dw_finish(const float*, int, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t, int64_t,
-                   int32_t, int32_t, float*, void*);
+                   int32_t, int32_t, float*, const float*, int, void*);
 int pcfd_thin_fwd_kind(const pcfd_intrans_t*, int32_t, int64_t, int32_t, int32_t);
 int pcfd_thin_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                              const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
@@ -48,7 +48,7 @@ int pcfd_ws_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int3
 int pcfd_ws_supported_dw(const float*, int64_t, int32_t, const float*, int64_t, int32_t, int32_t, int64_t, int32_t, int32_t);
 size_t pcfd_ws_dw_workspace_bytes(int32_t, int64_t, int64_t, int32_t, int32_t);
 int pcfd_ws_jet_linear_bwd_dw_partials(const float*, int64_t, int32_t, const float*, int64_t, int32_t,
-                                       const pcfd_intrans_t*, int32_t, int64_t, int64_t, int32_t, int32_t, void*, int*,
+                                       const pcfd_intrans_t*, int32_t, int64_t, int64_t, int32_t, int32_t, void*, int, int*,
                                        void*);
 int pcfd_ws_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
@@ -160,13 +160,15 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
 #ifdef PCFD_HAVE_TC
   if (g_engine == 2 && gw != nullptr && pcfd_ws_supported_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, cj, rows, k, n)) {
     int splits = 0;
+    const int fused_sums = gbias != nullptr && gcvec == nullptr;     // the dW kernel sums plane 0 of gzout on the way
     rc = pcfd_ws_jet_linear_bwd_dw_partials(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, cj, rows, rows_per_geom, k,
-                                            n, workspace, &splits, stream);
+                                            n, workspace, fused_sums, &splits, stream);
     if (rc) return rc;
     float* partial = reinterpret_cast<float*>(workspace);
-    float* tmp = partial + (size_t)splits * n * k;
+    float* colsum = partial + (size_t)splits * n * k;
+    float* tmp = colsum + (size_t)splits * n;
     return pcfd_dw_finish(partial, splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows, rows_per_geom, k, n, tmp,
-                          stream);
+                          fused_sums ? colsum : nullptr, splits, stream);
   }
   if (g_engine >= 1 && gw != nullptr && pcfd_tc_supported_bwd(cj, rows, k, n)) {
     int splits = 0;
@@ -176,7 +178,7 @@ extern "C" int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps, int3
     float* partial = reinterpret_cast<float*>(workspace);
     float* tmp = partial + (size_t)splits * n * k;
     return pcfd_dw_finish(partial, splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows, rows_per_geom, k, n, tmp,
-                          stream);
+                          nullptr, 0, stream);
   }
 #endif
   return pcfd_ffma_jet_linear_bwd_dw(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, tin, gw, ldgw, gbias, gcvec, ldgcvec,

@@ -117,15 +117,21 @@ using namespace pcfd;
 
 // tmp must hold chunks * ceil(rows_per_chunk / 128) * n floats (every engine's workspace query reserves
 // chunks * ceil(rows_per_chunk / 128) * n)
+// `colsum_partial` ([colsum_parts][n], optional): column sums of plane 0 of gzout already formed by the dW kernel
+// (engine 2); used for the bias gradient when no per-geometry gradient is wanted, instead of a pass over gzout.
 extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzout, int32_t ldgzout, float* gw,
                               int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec, int64_t rows,
-                              int64_t rows_per_geom, int32_t k, int32_t n, float* tmp, void* stream) {
+                              int64_t rows_per_geom, int32_t k, int32_t n, float* tmp, const float* colsum_partial,
+                              int colsum_parts, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool do_gw = gw != nullptr && partial != nullptr;
   const bool do_cs = gbias != nullptr || gcvec != nullptr;
   int64_t chunks = 0;
   int subs = 0;
-  if (do_cs) {
+  const float* sums = tmp;
+  if (do_cs && gcvec == nullptr && colsum_partial != nullptr) {
+    sums = colsum_partial; chunks = colsum_parts; subs = 1;
+  } else if (do_cs) {
     if (gcvec != nullptr && rows_per_geom <= 0) return PCFD_ERR_ARG;
     const int64_t rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
     chunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
@@ -141,7 +147,7 @@ extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzo
   if (do_gw || do_cs) {
     const int gw_blocks = do_gw ? (int)(((int64_t)n * k + 31) / 32) : 0;
     const int cs_blocks = do_cs ? (n + 31) / 32 : 0;
-    dw_finish_kernel<<<(unsigned)(gw_blocks + cs_blocks), 256, 0, st>>>(partial, splits, n, k, gw, ldgw, gw_blocks, tmp,
+    dw_finish_kernel<<<(unsigned)(gw_blocks + cs_blocks), 256, 0, st>>>(partial, splits, n, k, gw, ldgw, gw_blocks, sums,
                                                                         chunks, subs, gbias, gcvec, ldgcvec);
     PCFD_CHECK_LAUNCH();
   }

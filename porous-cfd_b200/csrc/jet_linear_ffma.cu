@@ -478,7 +478,7 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps,
 }
 
 extern "C" int pcfd_dw_finish(const float*, int, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t,
-                              int64_t, int32_t, int32_t, float*, void*);   // dw_finish.cu
+                              int64_t, int32_t, int32_t, float*, const float*, int, void*);   // dw_finish.cu
 
 extern "C" size_t pcfd_ffma_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   if (!valid_cj(cj) || rows <= 0 || k <= 0 || n <= 0) return 0;
@@ -511,5 +511,5 @@ extern "C" int pcfd_ffma_jet_linear_bwd_dw(const float* gzout, int64_t gzout_ps,
     PCFD_CHECK_LAUNCH();
   }
   return pcfd_dw_finish(gw != nullptr ? partial : nullptr, p.splits, gzout, ldgzout, gw, ldgw, gbias, gcvec, ldgcvec, rows,
-                        rows_per_geom, k, n, tmp, stream);
+                        rows_per_geom, k, n, tmp, nullptr, 0, stream);
 }

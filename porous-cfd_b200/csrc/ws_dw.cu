@@ -18,6 +18,8 @@
 //               reads the top 19 bits) and the exact remainders lo = x - trunc_tf32(x) of both operands;
 //               after the main loop the same warps drain the accumulators to the partial buffer
 //   warp 16     TMA producer, warp 17 MMA issuer (D += Ahi*Bhi + Alo*Bhi + Ahi*Blo)
+//   warp 18     column sums of the value plane of the staged gzout tile (the bias gradient), kept in registers over
+//               the whole row range and written as one partial row per split -- saves a second pass over gzout
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,8 +29,8 @@ namespace pcfd {
 namespace ws {
 
 constexpr int DW_GROUPS = 4, DW_GROUP = 128;
-constexpr int DW_W_TMA = DW_GROUPS * DW_GROUP / 32, DW_W_MMA = DW_W_TMA + 1;
-constexpr int DW_THREADS = (DW_W_MMA + 1) * 32;
+constexpr int DW_W_TMA = DW_GROUPS * DW_GROUP / 32, DW_W_MMA = DW_W_TMA + 1, DW_W_SUM = DW_W_TMA + 2;
+constexpr int DW_THREADS = (DW_W_SUM + 1) * 32;
 constexpr int DW_MAX_STAGES = 8;
 constexpr int DW_SMEM_MAX = 232448 - 2048;      // dynamic shared memory we may ask for (227 KB less static + alignment slack)
 
@@ -41,6 +43,7 @@ struct DwArgs {
   int passes_k;                 // passes along k (pass index = pn * passes_k + pk)
   int stages, groups;           // ring depth; transform groups in use (groups divides stages, see plan_dw)
   int vec_out;                  // k % 4 == 0: 16-byte stores into the partial buffer
+  float* colsum;                // optional [splits][n]: column sums of plane 0 of gzout over the split's rows
 };
 
 template <int CJ, int R, int NT>
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < STG; ++s) {
       tc::mbar_init(&raw_full[s], 1);
-      tc::mbar_init(&ops_ready[s], DW_GROUP);
+      tc::mbar_init(&ops_ready[s], DW_GROUP + (a.colsum != nullptr ? 32 : 0));
       tc::mbar_init(&stage_free[s], 1);
     }
     tc::mbar_init(&acc_full, 1);
@@ -138,6 +141,50 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
     }
     if (elect_one()) tc::mma_commit(&acc_full);
     __syncwarp();
+  } else if (warp == DW_W_SUM) {
+    // ================================ bias column sums ================================
+    // lane = (block within a group of 4, logical 16-byte chunk); rows of channel 0 only (contraction entries < R)
+    if (a.colsum != nullptr) {
+      const int jl = lane & 7, bl = lane >> 3;
+      float4 acc[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < nsteps; ++it) {
+        const uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        tc::bounded_wait(&raw_full[s], ph);
+        if (pk == 0) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int b = 4 * t + bl;
+            if (b < ab) {
+#pragma unroll
+              for (int e = 0; e < R; ++e) {
+                const uint32_t off = (uint32_t)e * 128u + (((((uint32_t)jl >> 1) ^ ((uint32_t)e & 3u)) << 5) | (((uint32_t)jl & 1u) << 4));
+                const float4 x = *reinterpret_cast<const float4*>(st + b * BLK + off);
+                acc[t].x += x.x; acc[t].y += x.y; acc[t].z += x.z; acc[t].w += x.w;
+              }
+            }
+          }
+        }
+        mbar_arrive(&ops_ready[s]);
+        if (++s == STG) { s = 0; ph ^= 1; }
+      }
+      if (pk == 0) {
+        float* dst = a.colsum + (int64_t)blockIdx.y * a.n;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = n0 + (4 * t + bl) * 32 + jl * 4;
+          if (4 * t + bl < ab) {
+            if (col < a.n) dst[col] = acc[t].x;
+            if (col + 1 < a.n) dst[col + 1] = acc[t].y;
+            if (col + 2 < a.n) dst[col + 2] = acc[t].z;
+            if (col + 3 < a.n) dst[col + 3] = acc[t].w;
+          }
+        }
+      }
+    }
   } else {
     // ================================ transform ================================
     const int g = warp >> 2;
@@ -377,19 +424,22 @@ extern "C" int pcfd_ws_supported_dw(const float* gzout, int64_t gzout_ps, int32_
 
 extern "C" size_t pcfd_ws_dw_workspace_bytes(int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n) {
   ws::DwPlan p = ws::plan_dw(cj, rows, rows_per_geom, k, n);
-  return ((size_t)p.splits * n * k + (size_t)p.chunks * ((p.rows_per_chunk + 127) / 128) * n) * sizeof(float) + 256;
+  return ((size_t)p.splits * n * k + (size_t)p.splits * n + (size_t)p.chunks * ((p.rows_per_chunk + 127) / 128) * n) *
+             sizeof(float) + 256;
 }
 
-// writes partial[splits][n][k] at the start of `workspace`; returns the number of splits through *splits_out
+// writes partial[splits][n][k] at the start of `workspace` and, when `want_colsum`, the column sums of plane 0 of
+// gzout per split right behind it ([splits][n]); returns the number of splits through *splits_out
 extern "C" int pcfd_ws_jet_linear_bwd_dw_partials(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* zin,
                                                   int64_t zin_ps, int32_t ldzin, const pcfd_intrans_t* tin, int32_t cj,
                                                   int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
-                                                  void* workspace, int* splits_out, void* stream) {
+                                                  void* workspace, int want_colsum, int* splits_out, void* stream) {
   ws::DwPlan p = ws::plan_dw(cj, rows, rows_per_geom, k, n);
   if (p.stages < 2) return PCFD_ERR_ARG;
   if (cj == 1) { gzout_ps = (int64_t)rows * ldgzout; zin_ps = (int64_t)rows * ldzin; }
   ws::DwArgs a{reinterpret_cast<float*>(workspace), rows, rows_per_geom, p.rows_per_split, k, n, make_intrans(tin, k),
-               p.mt, p.ntl, p.passes_k, p.stages, p.groups, (k % 4 == 0 && al16(workspace)) ? 1 : 0};
+               p.mt, p.ntl, p.passes_k, p.stages, p.groups, (k % 4 == 0 && al16(workspace)) ? 1 : 0,
+               want_colsum ? reinterpret_cast<float*>(workspace) + (size_t)p.splits * n * k : nullptr};
   *splits_out = p.splits;
   cudaStream_t st = (cudaStream_t)stream;
 #define PCFD_WS_DW(CJ_, R_)                                                                                    \
