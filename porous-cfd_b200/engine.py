@@ -214,6 +214,32 @@ class StepResult:
         return self.out[0:self.n_terms]
 
 
+class GraphedStep:
+    """One captured CUDA graph of `PinnExecutor.step` for a fixed input signature.  Inputs are copied into static
+    device buffers (device-to-device, a few microseconds), the ~130 kernels of the step replay as one launch, and the
+    results live in static buffers that stay valid until the next replay."""
+
+    def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str):
+        self.data = torch.empty_like(data)
+        self.domain = {k: torch.empty_like(v) for k, v in domain.items()}
+        self.labels = labels
+        self.load(data, domain)
+        torch.cuda.current_stream().synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = ex.step(self.data, labels, self.domain, laplacian)
+
+    def load(self, data: Tensor, domain: dict) -> None:
+        self.data.copy_(data, non_blocking=True)
+        for k, v in domain.items():
+            self.domain[k].copy_(v, non_blocking=True)
+
+    def run(self, data: Tensor, domain: dict) -> 'StepResult':
+        self.load(data, domain)
+        self.graph.replay()
+        return self.result
+
+
 class PinnExecutor:
     """Runs forward / training step of one model through the CUDA kernels.  Built lazily by
     `PorousPinnBase` once the model lives on a CUDA device."""
@@ -236,6 +262,8 @@ class PinnExecutor:
             self.ctx.grads[id(p)] = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.plan = model.build_plan()   # dict, see models/*.py
+        self._graphs: dict = {}
+        self._seen: set = set()
 
     # ---- helpers --------------------------------------------------------------------------
     def _cols(self, labels: dict, name: str):
@@ -394,6 +422,23 @@ class PinnExecutor:
         zs = chain_forward(ctx, plan['point_layers'], z0, n, escale, cvecs, salt_base=100)
         ops.end_step()
         return zs[-1].values().reshape(b, n, d + 1)
+
+    def graphed_step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference') -> StepResult:
+        """`step` replayed from a CUDA graph.  The first call with a given signature runs eagerly (it sizes the
+        workspace and the padded weight copies), the second captures, later ones replay; every call is exactly one
+        training step (dropout seed, ReLoBRaLo state and gradients advance once)."""
+        key = (tuple(data.shape), tuple((k, tuple(v.shape)) for k, v in sorted(domain.items())), tuple(labels),
+               laplacian, self.model.training, self.model.enable_data_loss)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g.run(data, domain)
+        if key not in self._seen:
+            self._seen.add(key)
+            return self.step(data, labels, domain, laplacian)
+        g = GraphedStep(self, data, labels, domain, laplacian)
+        self._graphs[key] = g
+        g.graph.replay()
+        return g.result
 
     def predict_with_residuals(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference'):
         """predict_step(verbose): predictions at all points (B, N, D+1) and the residual map of the internal

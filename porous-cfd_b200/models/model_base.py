@@ -55,6 +55,7 @@ class _StepGradients(torch.autograd.Function):
     def backward(ctx, grad_out):
         ex = ctx.executor
         scaled = ex.flat_grad * grad_out
+        ex.last_flat_grad = scaled      # every p.grad below is a view of this buffer: one all-reduce covers them all
         grads, off = [], 0
         for p in ex.params:
             grads.append(scaled[off:off + p.numel()].view_as(p))
@@ -71,6 +72,7 @@ class PorousPinnBase(_Base):
     def __init__(self, out_features: int, enable_data_loss=True, loss_scaler=None, laplacian: str = 'reference'):
         super().__init__()
         self.verbose_predict = False
+        self.cuda_graph = False        # training_step replays the fused step from a CUDA graph (per input signature)
         self.enable_data_loss = bool(enable_data_loss)
         self.dims = out_features - 1
         self.laplacian = laplacian
@@ -179,7 +181,10 @@ class PorousPinnBase(_Base):
         return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs)
 
     def training_step(self, batch: FoamData, batch_idx: int = 0):
-        res = self.fused_step(batch)
+        if self.cuda_graph:
+            res = self.executor.graphed_step(batch.data, batch.labels, batch.domain, self.laplacian)
+        else:
+            res = self.fused_step(batch)
         self.last_step = res
         loss = _StepGradients.apply(self.executor, res.loss, *self.executor.params)
         d = self.dims
