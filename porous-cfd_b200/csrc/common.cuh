@@ -29,11 +29,23 @@ struct ActD { float f0, f1, f2, f3; };
 // sigmoid / tanh on the SFU (ex2.approx + rcp): ~1e-6 relative error for |z| <= 10, two orders of
 // magnitude inside the 1e-4 parity budget, and ~4x fewer instructions than expf + IEEE division --
 // the input transform is on the critical path of the tensor-core kernels' operand staging.
-__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// Raw MUFU forms: ex2 saturates to +inf / 0 and rcp(+inf) = 0, so no range fix-up is needed (the __expf / __fdividef
+// wrappers add 3-4 instructions of it per call, which matters: the transform warps are issue-bound).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
 __device__ __forceinline__ float fast_tanh(float z) {
   const float z2 = z * z;
   if (z2 < 0.01f) return z * (1.0f + z2 * (-0.33333333f + z2 * (0.13333333f - z2 * 0.053968254f)));
-  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
+  return 1.0f - 2.0f * rcp_approx(1.0f + ex2_approx(2.8853900817779268f * z));
 }
 
 template <bool NEED3>

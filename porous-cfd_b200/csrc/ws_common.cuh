@@ -204,14 +204,14 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 
 // ---- device: input transform of a staged chunk ----------------------------------------------------
 // activation jet of the (up to) 4 columns of one staged 16-byte chunk, all channels
-template <int CJ, int ACT, bool SCALED>
-__device__ __forceinline__ void transform_chunk(float (&v)[CJ][4], const InTrans& tin, uint32_t hseed, int64_t row,
-                                                int64_t geom, int col0, int ncols) {
+template <int CJ, int ACT, bool SCALED, bool FULL>
+__device__ __forceinline__ void transform_chunk_impl(float (&v)[CJ][4], const InTrans& tin, uint32_t hseed, int64_t row,
+                                                     int64_t geom, int col0, int ncols) {
   uint32_t hrow = 0;
   if (SCALED && tin.drop_p > 0.0f) hrow = dropout_row_hash(hseed, row);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    if (e < ncols) {
+    if (FULL || e < ncols) {
       float sc = 1.0f;
       if (SCALED) {
         if (tin.drop_p > 0.0f) sc = dropout_from_row(hrow, row, col0 + e, tin.drop_p, tin.inv_keep);
@@ -225,6 +225,13 @@ __device__ __forceinline__ void transform_chunk(float (&v)[CJ][4], const InTrans
       for (int c = 0; c < CJ; ++c) v[c][e] = zz[c];
     }
   }
+}
+// all four columns active (the common case) takes the predicate-free path
+template <int CJ, int ACT, bool SCALED>
+__device__ __forceinline__ void transform_chunk(float (&v)[CJ][4], const InTrans& tin, uint32_t hseed, int64_t row,
+                                                int64_t geom, int col0, int ncols) {
+  if (ncols >= 4) transform_chunk_impl<CJ, ACT, SCALED, true>(v, tin, hseed, row, geom, col0, ncols);
+  else transform_chunk_impl<CJ, ACT, SCALED, false>(v, tin, hseed, row, geom, col0, ncols);
 }
 template <int CJ>
 __device__ __forceinline__ void transform_dispatch(float (&v)[CJ][4], const InTrans& tin, bool scaled, uint32_t hseed,
