@@ -258,6 +258,12 @@ int pcfd_relobralo_update(const float* losses, int32_t n, float* init_losses, fl
                           int64_t* step, int32_t batch_size, float alpha, float beta, float tau, float eps,
                           uint64_t seed, float* weights_out, void* stream);
 
+/* torch.optim.Adam (no weight decay, no amsgrad; models/pipn/pipn_foam.py:102-105 configure_optimizers) on flat
+ * fp32 buffers: step += 1; m, v, param updated in one pass.  `step` (int64) and `lr` (float) are device scalars so
+ * that the launch is graph-capturable; `grad_scale` multiplies the gradient first (1/world after an all-reduce). */
+int pcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                   const float* lr, float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream);
+
 /* out[i] = 0 for i < n (graph-capturable memset of gradient buffers) */
 int pcfd_zero(float* p, int64_t n, void* stream);
 /* *seed_dev = mix(*seed_dev) : advances the dropout seed once per step without a host round trip */

@@ -70,25 +70,34 @@ class FlatAdamTrainer:
             dist.broadcast(self.flat_param, 0, group=self.group)
         opt_cfg = model.configure_optimizers()[0][0]
         g = opt_cfg.param_groups[0]
-        self.master = torch.nn.Parameter(self.flat_param)
-        self.master.grad = ex.flat_grad
-        self.optimizer = torch.optim.Adam([self.master], lr=g['lr'], betas=g['betas'], eps=g['eps'], fused=True)
-        gamma = model.configure_optimizers()[1][0]['scheduler'].gamma
-        self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, gamma)
+        self.betas, self.eps = g['betas'], g['eps']
+        self.gamma = model.configure_optimizers()[1][0]['scheduler'].gamma
+        # Adam state on the device (step and learning rate included): the update is one kernel, graph-capturable
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=ex.device)
+        self.lr_dev = torch.full((1,), float(g['lr']), dtype=torch.float32, device=ex.device)
+        self.optimizer = self     # `.optimizer.step()` of the earlier torch.optim-based trainer keeps working
 
     def reduce_gradients(self):
         if self.world > 1:
             dist.all_reduce(self.model.executor.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-            self.model.executor.flat_grad.mul_(1.0 / self.world)
+
+    def step(self):
+        """Adam (torch.optim.Adam semantics) on the flat buffers; 1/world of the all-reduce is folded in."""
+        from .. import ops
+        ops.adam_step(self.flat_param, self.model.executor.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
+                      self.lr_dev, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
 
     def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
         res = self.model.fused_step(batch, laplacian)
         self.reduce_gradients()
-        self.optimizer.step()
+        self.step()
         return res
 
     def end_epoch(self):
-        self.scheduler.step()
+        """ExponentialLR, interval = epoch (reference models/pipn/pipn_foam.py:102-105)."""
+        self.lr_dev.mul_(self.gamma)
 
 
 def shard_batch(batch: FoamData, rank: int, world: int) -> FoamData:

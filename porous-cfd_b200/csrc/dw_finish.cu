@@ -74,9 +74,16 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
     const int64_t idx = (int64_t)blockIdx.x * 32 + lane;
     float s = 0.0f;
     if (idx < total) {
-      int sp = wy;
-      for (; sp + 8 < splits; sp += 16) s += partial[(int64_t)sp * total + idx] + partial[(int64_t)(sp + 8) * total + idx];
-      for (; sp < splits; sp += 8) s += partial[(int64_t)sp * total + idx];
+      // five independent loads in flight per thread: the reduction is latency-bound (splits / 8 values per thread)
+      for (int base = wy; base < splits; base += 40) {
+        float v[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int sp = base + 8 * u;
+          v[u] = sp < splits ? __ldg(partial + (int64_t)sp * total + idx) : 0.0f;
+        }
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+      }
     }
     red[wy][lane] = s;
     __syncthreads();
@@ -92,7 +99,17 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
   // ---- column sums: column = (blockIdx.x - gw_blocks) * 32 + lane, chunk lane wy
   const int col = ((int)blockIdx.x - gw_blocks) * 32 + lane;
   float s = 0.0f;
-  if (col < n) {
+  if (col < n && subs == 1 && gcvec == nullptr) {
+    for (int64_t base = wy; base < chunks; base += 40) {
+      float v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int64_t c = base + 8 * u;
+        v[u] = c < chunks ? __ldg(tmp + c * n + col) : 0.0f;
+      }
+      s += ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+    }
+  } else if (col < n) {
     for (int64_t c = wy; c < chunks; c += 8) {
       const float* p = tmp + c * subs * n + col;
       float v = 0.0f;
@@ -111,9 +128,48 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
   }
 }
 
+// Adam on flat fp32 buffers (torch.optim.Adam semantics, no weight decay / amsgrad): one elementwise pass instead of
+// torch's multi-tensor kernel, which cuts a single 861k-element tensor into 14 chunks (39 us vs ~5 us).  `step` and `lr`
+// live on the device so the launch is graph-capturable and the scheduler can change the rate between replays.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, const int64_t* step, const float* lr, float b1,
+                                                   float b2, float eps, float grad_scale, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float t = (float)(*step);
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
+  const float step_size = *lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (i + e < n) {
+      const float gr = g[i + e] * grad_scale;
+      const float mm = b1 * m[i + e] + (1.0f - b1) * gr;
+      const float vv = b2 * v[i + e] + (1.0f - b2) * gr * gr;
+      m[i + e] = mm;
+      v[i + e] = vv;
+      p[i + e] -= step_size * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+    }
+  }
+}
+
+__global__ void adam_advance_kernel(int64_t* step) { *step += 1; }
+
 }  // namespace pcfd
 
 using namespace pcfd;
+
+extern "C" int pcfd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t* step,
+                              const float* lr, float beta1, float beta2, float eps, float grad_scale, int64_t n,
+                              void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || !lr || n <= 0) return PCFD_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_advance_kernel<<<1, 1, 0, st>>>(step);
+  PCFD_CHECK_LAUNCH();
+  adam_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps,
+                                                            grad_scale, n);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
 
 // tmp must hold chunks * ceil(rows_per_chunk / 128) * n floats (every engine's workspace query reserves
 // chunks * ceil(rows_per_chunk / 128) * n)

@@ -16,6 +16,8 @@
 //                segment, all channels per thread) applies the reverse jet against coalesced loads of
 //                zin and writes gzin with coalesced 16-byte stores.  Layers without an input transform
 //                skip phase 2 and TMA-store the staging tile.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ws_common.cuh"
 
@@ -76,6 +78,7 @@ struct DxArgs {
   int64_t rows, rows_per_geom; int k, n;
   InTrans tin;
   int row_tiles, k_passes;
+  int dbg;   // PCFD_WS_DEBUG bit mask (timing experiments): 8 skip the reverse-jet math, 16 skip phase 2, 32 skip the gzin stores
 };
 
 template <int CJ, int NT>
@@ -331,14 +334,14 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
           for (int i = 0; i < ITEMS; ++i) {
             const int pgi = pgsel + 2 * i;
             const int64_t row = row0 + pgi * 32 + r;
-            if (!(pgi < PGS && cvalid && row < a.rows)) continue;
+            if (!(pgi < PGS && cvalid && row < a.rows) || (a.dbg & 16)) continue;
             float gq[CJ][4];
 #pragma unroll
             for (int c = 0; c < CJ; ++c) {
               const float4 x = *reinterpret_cast<const float4*>(stg + (pgi * CJ + c) * 4096 + swz<128>(r, j));
               gq[c][0] = x.x; gq[c][1] = x.y; gq[c][2] = x.z; gq[c][3] = x.w;
             }
-            if (col < a.tin.act_cols) {
+            if (col < a.tin.act_cols && !(a.dbg & 8)) {
               const int64_t geom = uniform ? g_first : geom_of(row, a.rows_per_geom);
               float ge[4] = {0.f, 0.f, 0.f, 0.f};
               reverse_dispatch<CJ>(gq, z[i], a.tin, scaled, hseed, row, geom, col, a.tin.act_cols - col, ge);
@@ -350,10 +353,12 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
                 }
               }
             }
+            if (!(a.dbg & 32)) {
 #pragma unroll
-            for (int c = 0; c < CJ; ++c)
-              *reinterpret_cast<float4*>(a.gzin + c * a.gzin_ps + row * a.ldgzin + col) =
-                  make_float4(gq[c][0], gq[c][1], gq[c][2], gq[c][3]);
+              for (int c = 0; c < CJ; ++c)
+                *reinterpret_cast<float4*>(a.gzin + c * a.gzin_ps + row * a.ldgzin + col) =
+                    make_float4(gq[c][0], gq[c][1], gq[c][2], gq[c][3]);
+            }
           }
           if (a.gescale != nullptr && uniform) {
 #pragma unroll
@@ -411,6 +416,9 @@ static int launch_dx(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
   }
   a.row_tiles = (int)((a.rows + POINTS - 1) / POINTS);
   a.k_passes = (a.k + NT - 1) / NT;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PCFD_WS_DEBUG"); dbg = e ? atoi(e) : 0; }
+  a.dbg = dbg;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(ws_dx_kernel<CJ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -449,7 +457,7 @@ extern "C" int pcfd_ws_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, i
                                          int64_t rows_per_geom, int32_t k, int32_t n, void* stream) {
   if (cj == 1) { gzout_ps = (int64_t)rows * ldgzout; zin_ps = (int64_t)rows * ldzin; gzin_ps = (int64_t)rows * ldgzin; }
   ws::DxArgs a{zin, zin_ps, ldzin, gzin, gzin_ps, ldgzin, gescale, ldgescale, rows, rows_per_geom, k, n,
-               make_intrans(tin, k), 0, 0};
+               make_intrans(tin, k), 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
 #define PCFD_WS_DX(CJ_)                                                             \
   return k <= 64 ? ws::launch_dx<CJ_, 64>(gzout, gzout_ps, ldgzout, w, ldw, a, st)  \

@@ -355,6 +355,14 @@ def relobralo_update(losses: Tensor, n: int, init_losses: Tensor, prev_losses: T
                                     weights_out.data_ptr(), _stream()), 'pcfd_relobralo_update')
 
 
+def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor, lr: Tensor,
+              beta1: float, beta2: float, eps: float, grad_scale: float = 1.0) -> None:
+    lib = _lib.load()
+    _lib.launches += 2
+    check(lib.pcfd_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), step.data_ptr(),
+                             lr.data_ptr(), beta1, beta2, eps, grad_scale, param.numel(), _stream()), 'pcfd_adam_step')
+
+
 def zero_(t: Tensor) -> None:
     lib = _lib.load()
     _lib.launches += 1

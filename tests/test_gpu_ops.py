@@ -292,3 +292,26 @@ def test_relobralo_kernel_matches_reference_vectors(ops, case):
         got = (w[:n] * losses).cpu()
         assert max_rel(got, torch.from_numpy(z[f'{case}/weighted'][s])) < 1e-5, (case, s)
     assert int(step.item()) == steps
+
+
+def test_fused_adam_matches_torch(ops):
+    """pcfd_adam_step against torch.optim.Adam (models/pipn/pipn_foam.py:102-105) on a flat buffer, 4 steps,
+    learning rate changed in between (ExponentialLR)."""
+    g = torch.Generator().manual_seed(5)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().cuda())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device='cuda')
+    lr = torch.full((1,), 1e-3, device='cuda')
+    for it in range(4):
+        grad = torch.randn(n, generator=g).cuda() * (10.0 ** (it - 2))
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, grad * 4.0, m, v, step, lr, 0.9, 0.999, 1e-8, 0.25)     # grad_scale undoes the factor 4
+        assert rel_l2(p.double().cpu(), ref.detach().double().cpu()) < 1e-6
+        opt.param_groups[0]['lr'] *= 0.999
+        lr.mul_(0.999)
+    assert int(step.item()) == 4
