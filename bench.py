@@ -50,6 +50,8 @@ N_BATCHES = 4            # distinct synthetic batches cycled through
 # BASELINE.json configs 2-5 (config 2 is the default: the one the metric is quoted on for one GPU).  The others are
 # selectable with --config for DESIGN.md's per-config table; their parity is covered by tests/.
 WORKLOADS = {
+    'abc_pipn': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=13,
+                     what='PIPN abc 3-D, vanilla (examples/abc/train.py:26-34; max-pool coupling terms included)'),
     'abc_pipn_pp': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=32,
                         what='PIPN++ abc 3-D (examples/abc/train.py:36-49)'),
     'duct_pigano': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=64,

@@ -233,12 +233,15 @@ int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_rows, int32_
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* pcfd_residual_loss with DEVICE-resident loss weights (`weights_dev`, one float per loss term; NULL = prm->weights):
- * the weights of an adaptive scaler change every step without re-recording a captured graph. */
+ * the weights of an adaptive scaler change every step without re-recording a captured graph.
+ * `visc_extra` (optional, [n_geom*ni][D]) is added to the Laplacian row sums of the momentum residual and `gvisc`
+ * (optional, same shape) receives d loss / d visc_extra: the cross-point terms of vanilla PIPN (coupling.py). */
 int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
                          const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
                          const int64_t* obs_ids, int64_t no,
                          const float* y_int, int64_t y_plane_stride, const float* y_bnd, int32_t ldy,
                          const pcfd_residual_params_t* prm_host, const float* weights_dev,
+                         const float* visc_extra, float* gvisc,
                          float* gy_int, float* gy_bnd, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 

@@ -73,7 +73,7 @@ SIGNATURES = {
     'pcfd_residual_loss': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
                                      C.POINTER(ResidualParams), _P, _P, _P, _P, _SZ, _P]),
     'pcfd_residual_loss_w': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
-                                       C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _SZ, _P]),
+                                       C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
     'pcfd_adam_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     'pcfd_relobralo_update': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F, _F, _F, _F, C.c_uint64, _P, _P]),

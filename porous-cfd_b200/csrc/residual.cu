@@ -25,6 +25,8 @@ struct ResArgs {
   float* partial;                     // this kernel's [blocks][NSLOT]
   const float* wdev;                  // optional device-resident loss weights (ReLoBRaLo); else p.weights
   float* fields;                      // optional per-point residual map [n_geom*ni][D+1] = (momentum xD, div)
+  const float* visc_extra;            // optional [n_geom*ni][D]: added to the Laplacian row sums (vanilla-PIPN coupling)
+  float* gvisc;                       // optional [n_geom*ni][D]: d loss / d visc_extra
 };
 
 #define PCFD_WT(i) (a.wdev != nullptr ? __ldg(a.wdev + (i)) : P.weights[i])
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
 #pragma unroll
         for (int j = 0; j < D; ++j) visc += y[1 + j][j] * (1.0f / (sx[j] * sx[j]));
       }
+      if (a.visc_extra != nullptr) visc += __ldg(a.visc_extra + t * D + c);
       visc *= P.nu * su[c];
       const float pres = (sp / sx[c]) * y[1 + c][D];
       const float source = ur[c] * (dcoef[c] * P.nu + 0.5f * nrm * fcoef[c]);
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
         gur[j] += gr[c] * su[c] * y[1 + j][c] / sx[j];            // d conv_c / d u_raw_j
       }
       const float gv = -gr[c] * P.nu * su[c];
+      if (a.gvisc != nullptr) a.gvisc[t * D + c] = gv;
       if (LAP == PCFD_LAP_TRUE) {
 #pragma unroll
         for (int j = 0; j < D; ++j) gy[1 + D + j < CJ ? 1 + D + j : 0][c] += gv * (1.0f / (sx[j] * sx[j]));
@@ -298,8 +302,8 @@ extern "C" int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n
                                     const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
                                     const int64_t* obs_ids, int64_t no, const float* y_int, int64_t y_plane_stride,
                                     const float* y_bnd, int32_t ldy, const pcfd_residual_params_t* prm,
-                                    const float* weights_dev, float* gy_int, float* gy_bnd, float* out, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    const float* weights_dev, const float* visc_extra, float* gvisc, float* gy_int,
+                                    float* gy_bnd, float* out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!data || !internal_ids || !boundary_ids || !y_int || !y_bnd || !prm || !gy_int || !gy_bnd || !out || !workspace)
     return PCFD_ERR_ARG;
   if (n_geom <= 0 || ni <= 0 || nb <= 0 || (prm->dims != 2 && prm->dims != 3) || ldy < prm->dims + 1) return PCFD_ERR_ARG;
@@ -311,7 +315,7 @@ extern "C" int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n
   a.data = data; a.n_rows = n_rows; a.f = f;
   a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = boundary_ids; a.nb = nb; a.obs_ids = obs_ids; a.no = no;
   a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = y_bnd; a.ldy = ldy; a.gy_int = gy_int; a.gy_bnd = gy_bnd;
-  a.p = *prm; a.n_geom = n_geom; a.wdev = weights_dev; a.fields = nullptr;
+  a.p = *prm; a.n_geom = n_geom; a.wdev = weights_dev; a.fields = nullptr; a.visc_extra = visc_extra; a.gvisc = gvisc;
   a.inv_int = 1.0f / (float)((double)n_geom * ni);
   a.inv_bnd = 1.0f / (float)((double)n_geom * nb);
   a.inv_obs = no > 0 ? 1.0f / (float)((double)n_geom * no) : 0.0f;
@@ -357,8 +361,8 @@ extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_r
                                   float* gy_int, float* gy_bnd, float* out, void* workspace, size_t workspace_bytes,
                                   void* stream) {
   return pcfd_residual_loss_w(data, n_geom, n_rows, f, internal_ids, ni, boundary_ids, nb, obs_ids, no, y_int,
-                              y_plane_stride, y_bnd, ldy, prm, nullptr, gy_int, gy_bnd, out, workspace, workspace_bytes,
-                              stream);
+                              y_plane_stride, y_bnd, ldy, prm, nullptr, nullptr, nullptr, gy_int, gy_bnd, out, workspace,
+                              workspace_bytes, stream);
 }
 
 // Per-point residual map of the internal points (predict_step with verbose_predict, models/model_base.py:233-252):
@@ -374,6 +378,7 @@ extern "C" int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n
   a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = nullptr; a.nb = 0; a.obs_ids = nullptr; a.no = 0;
   a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = nullptr; a.ldy = ldy; a.gy_int = nullptr; a.gy_bnd = nullptr;
   a.p = *prm; a.n_geom = n_geom; a.wdev = nullptr; a.fields = fields; a.partial = nullptr;
+  a.visc_extra = nullptr; a.gvisc = nullptr;
   a.inv_int = 1.0f / (float)((double)n_geom * ni); a.inv_bnd = 0.0f; a.inv_obs = 0.0f;
   const int b_int = blocks_for((int64_t)n_geom * ni);
   const int D = prm->dims;

@@ -240,6 +240,16 @@ class GraphedStep:
         return self.result
 
 
+class _EagerStep:
+    """Stand-in for GraphedStep when capture is not possible."""
+
+    def __init__(self, ex, labels, laplacian):
+        self.ex, self.labels, self.laplacian = ex, labels, laplacian
+
+    def run(self, data, domain):
+        return self.ex.step(data, self.labels, domain, self.laplacian)
+
+
 class PinnExecutor:
     """Runs forward / training step of one model through the CUDA kernels.  Built lazily by
     `PorousPinnBase` once the model lives on a CUDA device."""
@@ -435,7 +445,15 @@ class PinnExecutor:
         if key not in self._seen:
             self._seen.add(key)
             return self.step(data, labels, domain, laplacian)
-        g = GraphedStep(self, data, labels, domain, laplacian)
+        try:
+            g = GraphedStep(self, data, labels, domain, laplacian)
+        except RuntimeError as exc:      # an op that cannot be captured: stay on the per-kernel launches for this signature
+            import warnings
+            warnings.warn(f'CUDA graph capture of the fused step failed ({exc}); launching eagerly')
+            torch.cuda.synchronize()
+            self._seen.discard(key)
+            self._graphs[key] = _EagerStep(self, labels, laplacian)
+            return self._graphs[key].run(data, domain)
         self._graphs[key] = g
         g.graph.replay()
         return g.result
@@ -494,6 +512,13 @@ class PinnExecutor:
         zs_int = chain_forward(ctx, layers, z0_int, ni, escale, cvecs, salt_base=100)
         zs_bnd = chain_forward(ctx, layers, z0_bnd, nb, escale, cvecs, salt_base=200)
 
+        coup = None
+        if plan['family'] == 'pipn' and laplacian == 'reference' and getattr(model, 'coupling', True):
+            # vanilla PIPN: max-pool cross-point terms of the reference's summed-output Jacobian (coupling.py)
+            from . import coupling
+            coup = coupling.forward(self, data, labels, int_ids, zs_int, saved, cj,
+                                    list(model.residual_params(labels, laplacian).c_std))
+
         prm = model.residual_params(labels, laplacian)
         ctx.need_workspace(ops.residual_workspace_bytes(b, ni, nb, obs_ids.shape[1] if obs_ids is not None else 0))
         scaler = getattr(model, 'loss_scaler', None)
@@ -508,7 +533,9 @@ class PinnExecutor:
                                  scaler.batch_size, scaler.alpha, scaler.beta, scaler.tau, scaler.eps, scaler.seed,
                                  weights_dev)
         gy_int, gy_bnd, out = ops.residual_loss(data, int_ids, bnd_ids, obs_ids, zs_int[-1], zs_bnd[-1], prm,
-                                                ctx.workspace, weights_dev)
+                                                ctx.workspace, weights_dev,
+                                                coup.visc_extra if coup is not None else None,
+                                                coup.gvisc if coup is not None else None)
 
         gcvecs = {'concat': torch.empty_like(cvecs['concat'])}
         ops.zero_(gcvecs['concat'])
@@ -518,6 +545,9 @@ class PinnExecutor:
             ops.zero_(gescale)
         chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100)
         chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200)
+        if coup is not None:
+            from . import coupling
+            coupling.backward(self, coup, data, int_ids, zs_int, gy_int, saved, gcvecs)
         self._encode_backward(saved, gcvecs, gescale)
         ops.end_step()
 

@@ -311,7 +311,8 @@ def residual_workspace_bytes(n_geom: int, ni: int, nb: int, no: int) -> int:
 
 
 def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_ids: Optional[Tensor],
-                  y_int: Jet, y_bnd: Jet, prm: ResidualParams, workspace: Tensor, weights_dev: Optional[Tensor] = None):
+                  y_int: Jet, y_bnd: Jet, prm: ResidualParams, workspace: Tensor, weights_dev: Optional[Tensor] = None,
+                  visc_extra: Optional[Tensor] = None, gvisc: Optional[Tensor] = None):
     """-> (gy_int Jet, gy_bnd Jet, out float32[48]).  `weights_dev`: device-resident loss weights (adaptive
     scaler) instead of prm.weights."""
     lib = _lib.load()
@@ -325,7 +326,8 @@ def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_
     with _timed('residual_loss', 8.0 * b * ni * y_int.cj * y_int.ld + 4.0 * b * ni * f + 8.0 * b * nb * y_int.ld):
       check(lib.pcfd_residual_loss_w(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
                                    nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
-                                   y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), _ptr(weights_dev), gy_int.t.data_ptr(),
+                                   y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), _ptr(weights_dev), _ptr(visc_extra),
+                                   _ptr(gvisc), gy_int.t.data_ptr(),
                                    gy_bnd.t.data_ptr(), out.data_ptr(), workspace.data_ptr(),
                                    workspace.numel() * workspace.element_size(), _stream()), 'pcfd_residual_loss_w')
     return gy_int, gy_bnd, out

@@ -52,26 +52,79 @@ def test_step_matches_reference_fixture(name, mode):
 
 
 @pytest.mark.parametrize('name', COUPLED)
-def test_vanilla_pipn_values_match_and_coupling_gap_is_known(name):
-    """Vanilla PIPN: predictions, boundary/observation losses (value path) match the reference; the
-    Jacobian-dependent terms differ by the max-pool cross-point coupling that the forward-mode jet
-    does not carry yet ('next' row 1)."""
+def test_vanilla_pipn_step_matches_reference_fixture(name):
+    """Vanilla PIPN, training_step as written: the reference's summed-output Jacobian, grad p and single-point
+    "Laplacian" contain max-pool cross-point terms; coupling.py adds them to the
+    forward-mode jets and differentiates them (a second, directional jet pass).  Every loss term and every parameter
+    gradient against the outputs of the UNMODIFIED reference."""
     spec = synthetic.model_spec(name)
     data, domain, params, out = load_fixture(name)
     labels = synthetic.build_labels(spec['layout'])
     model = cuda_model(spec, params)
-    res, _ = run_step(model, data, labels, domain, 'reference')
-    d = spec['dims']
-    ref = out['reference']['losses']
-    assert max_rel(res.losses[1 + d:2 + 2 * d], ref[1 + d:2 + 2 * d]) < TOL       # boundary terms
-    if spec['enable_data_loss']:
-        assert max_rel(res.losses[2 + 2 * d:], ref[2 + 2 * d:]) < TOL             # observation terms
-    # forward values against the oracle
+    res, grads = run_step(model, data, labels, domain, 'reference')
+    ref = out['reference']
+    assert max_rel(res.losses, ref['losses']) < TOL
+    assert abs(float(res.loss) - float(ref['loss'])) / abs(float(ref['loss'])) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(ref['grads'], keys)) < TOL
+    for k in keys:      # per tensor as well: no parameter group hides behind a larger one
+        assert rel_l2(grads[k].double().cpu().flatten(), ref['grads'][k].double().flatten()) < TOL, k
+    # what get_jacobian / calculate_gradients return in the reference
     batch = FoamData(data, labels, domain).to('cuda')
+    jets = model.jets(batch, 'reference')
+    orc = pinn_oracle.training_step(spec, params, data, labels, domain, 'reference')
+    assert rel_l2(jets['jacobian'].cpu().double(), orc['jac'].detach().double()) < TOL
+    assert rel_l2(jets['d_p'].cpu().double(), orc['dp'].detach().double()) < TOL
+    # forward values
     pts = torch.cat([batch['internal']['C'], batch['boundary']['C']], dim=1)
     y = model.forward(pts, batch).data.cpu()
     y_ref = pinn_oracle.forward(spec, params, pts.cpu(), data, labels, domain)
     assert rel_l2(y.double(), y_ref.double()) < 1e-5
+
+
+@pytest.mark.parametrize('name', COUPLED)
+def test_vanilla_pipn_documented_laplacian_gap_is_known(name):
+    """laplacian='true' (get_laplacian(points, get_jacobian(points, U))) for vanilla PIPN would need the SECOND-order
+    cross-point terms; they are not carried: value-path terms match, the derivative terms are the per-point ones."""
+    spec = synthetic.model_spec(name)
+    data, domain, params, out = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    res, _ = run_step(model, data, labels, domain, 'true')
+    d = spec['dims']
+    ref = out['true']['losses']
+    assert max_rel(res.losses[1 + d:2 + 2 * d], ref[1 + d:2 + 2 * d]) < TOL       # boundary terms
+    if spec['enable_data_loss']:
+        assert max_rel(res.losses[2 + 2 * d:], ref[2 + 2 * d:]) < TOL             # observation terms
+
+
+FULL_COUPLED = [  # config 1 (PipnFoam abc) and the vanilla branch of config 5, full layer widths, reduced point counts
+    ('abc_pipn', 2, 300, 200, 100, 0.05),
+    ('manufactured_pipn', 2, 256, 64, 0, 0.01),
+]
+
+
+@pytest.mark.parametrize('case', FULL_COUPLED)
+def test_full_width_vanilla_pipn_matches_oracle(case):
+    name, b, ni, nb, no, nu = case
+    spec = synthetic.model_spec(name)
+    spec['nu'] = nu
+    torch.manual_seed(3)
+    model = factory.build_model(spec)
+    params = synthetic.rescale_weights({k: v.detach().clone() for k, v in model.state_dict().items()}, 2.0)
+    model.load_state_dict(params)
+    model = model.to('cuda').eval()
+    for seed in range(17, 40):
+        data, labels, domain = synthetic.make_batch(spec['layout'], b, ni, nb, no, seed=seed)
+        pyg_restate.MARGINS = []
+        orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, 'reference')
+        margins, pyg_restate.MARGINS = pyg_restate.MARGINS, None
+        if not margins or min(margins) > 2e-5:
+            break
+    res, grads = run_step(model, data, labels, domain, 'reference')
+    assert max_rel(res.losses, orc['losses']) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(orc['grads'], keys)) < TOL
 
 
 @pytest.mark.parametrize('name', PER_POINT)
