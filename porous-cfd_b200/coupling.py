@@ -57,10 +57,10 @@ def _concat_index(layers) -> int:
     return next(i for i, L in enumerate(layers) if L.cvec_key == 'concat')
 
 
-def decoder_vjp(ex, zs, rows_per_geom: int, gz: Jet, salt_base: int, n_geom: int) -> Tensor:
+def decoder_vjp(ex, zs, rows_per_geom: int, gz: Jet, salt_base: int, n_geom: int, keep_rows: Optional[Tensor] = None):
     """Value-only reverse sweep through the decoder layers above the concat layer: gz [1][rows][n_out] cotangent of
-    the outputs -> per-geometry column sums of the cotangent of the concat layer's pre-activation, [n_geom, n_concat].
-    No parameter gradient is touched."""
+    the outputs -> per-geometry column sums of the cotangent of the concat layer's pre-activation, [n_geom, n_concat]
+    (and, with `keep_rows`, that cotangent at the given rows).  No parameter gradient is touched."""
     from .engine import _tin
     ctx, layers = ex.ctx, ex.plan['point_layers']
     ci = _concat_index(layers)
@@ -72,6 +72,8 @@ def decoder_vjp(ex, zs, rows_per_geom: int, gz: Jet, salt_base: int, n_geom: int
     out = torch.zeros((n_geom, ops.round4(Lc.n)), dtype=torch.float32, device=gz.t.device)
     ctx.need_workspace(ops.dw_workspace_bytes(1, gz.rows, rows_per_geom, Lc.k, Lc.n))
     ops.jet_linear_bwd_dw(gz, _plane0(zs[ci]), None, None, 0, None, out, rows_per_geom, Lc.k, Lc.n, ctx.workspace)
+    if keep_rows is not None:
+        return out, gz.t[0].index_select(0, keep_rows)
     return out
 
 
@@ -131,11 +133,16 @@ def forward(ex, data: Tensor, labels: dict, int_ids: Tensor, zs_int, saved: dict
     cl = plan['concat_layer']
     gjet = saved['gjet']
     S, st.gcv = [], []
+    geom_first = torch.arange(b, device=data.device) * ni
+    first_rows = (geom_first[None, :] + torch.arange(d, device=data.device)[:, None]).reshape(-1)   # (point i, geometry b)
+    single = []       # per output j: cotangent of the concat pre-activation at the first D points of every geometry
     for i in range(d + 1):
         gz = Jet.empty(1, y.rows, y.width, data.device)
         ops.zero_(gz.t)
         gz.t[0, :, i] = 1.0
-        gcv = decoder_vjp(ex, zs_int, ni, gz, 100, b)
+        gcv, r_first = decoder_vjp(ex, zs_int, ni, gz, 100, b, first_rows)
+        if i < d:
+            single.append(r_first)      # the decoder is per-point: row (b, i) of this sweep IS dU_i... /dp at that single point
         st.gcv.append(gcv)
         s_i = ops.jet_linear_bwd_dx(Jet(gcv.unsqueeze(0), cl.n), cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
         S.append(s_i.t[0, :, :g_width].reshape(-1))
@@ -158,21 +165,17 @@ def forward(ex, data: Tensor, labels: dict, int_ids: Tensor, zs_int, saved: dict
         ex._coupling_w = torch.tensor([1.0 / float(v) ** 2 for v in c_std[:d]], dtype=torch.float32, device=data.device)
     st.w = ex._coupling_w
     st.local_row = torch.where(internal, arg, torch.zeros_like(arg)).reshape(-1)
-    s1, st.gcv1 = [], []
-    geom_first = torch.arange(b, device=data.device) * ni
-    for i in range(d):              # point i of every geometry
-        row_s, row_g = [], []
-        for j in range(d):          # output component j
-            gz = Jet.empty(1, y.rows, y.width, data.device)
-            ops.zero_(gz.t)
-            gz.t[0, :, j].index_fill_(0, geom_first + i, 1.0)
-            gcv = decoder_vjp(ex, zs_int, ni, gz, 100, b)
-            row_g.append(gcv)
-            s_ij = ops.jet_linear_bwd_dx(Jet(gcv.unsqueeze(0), cl.n), cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
-            row_s.append(s_ij.t[0, :, :g_width].reshape(-1))
-        s1.append(torch.stack(row_s))
-        st.gcv1.append(row_g)
-    st.s1 = torch.stack(s1)                                                      # [i, j, B*G]
+    # s^(i)_j = dU_j(point i)/dg: the sweep for output j above already holds dU_j(m)/dp_m at EVERY row m (the decoder
+    # acts per point), so the single-point sensitivities are its rows (b, i) times W_g -- no further sweeps
+    ldc = ops.round4(cl.n)
+    r_all = torch.stack(single)                                                  # [j, D*B (i major), ld]
+    r_all = r_all.reshape(d, d, b, -1).permute(1, 0, 2, 3).contiguous()          # [i, j, B, ld]
+    st.gcv1 = [[r_all[i, j] for j in range(d)] for i in range(d)]
+    s_flat = ops.jet_linear_bwd_dx(Jet(r_all.reshape(1, d * d * b, -1), cl.n), cl.weight, cl.col_lo,
+                                   Jet(torch.empty((1, d * d * b, ops.round4(cl.k)), dtype=torch.float32, device=data.device), cl.k),
+                                   None, None, 0, cl.k, cl.n)
+    s1 = s_flat.t[0, :, :g_width].reshape(d, d, b * g_width)
+    st.s1 = s1                                                                   # [i, j, B*G]
     vx = torch.zeros((b * ni, d), dtype=torch.float32, device=data.device)
     add = (st.s1 * (st.w[None, :, None] * hk[None, :, :])).sum(1)               # [i, B*G]: sum_j w_j s^(i)_jc H_cj
     vx.index_put_((st.rows[None, :].expand_as(add), torch.arange(d, device=data.device)[:, None].expand_as(add)), add,
