@@ -68,6 +68,7 @@ class StepContext:
         self.training = False
         self.grads: dict[int, Tensor] = {}
         self.salt = 0
+        self.side_stream = None
 
     def need_workspace(self, nbytes: int):
         if self.workspace.numel() < nbytes:
@@ -505,12 +506,25 @@ class PinnExecutor:
         if ctx.training:
             ops.advance_seed(ctx.seed_dev)
 
-        cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None)
-        z0_int = ops.seed_jet(data, int_ids, ni, c_cols, cj)
-        z0_bnd = ops.seed_jet(data, bnd_ids, nb, c_cols, 1)
         layers = plan['point_layers']
-        zs_int = chain_forward(ctx, layers, z0_int, ni, escale, cvecs, salt_base=100)
-        zs_bnd = chain_forward(ctx, layers, z0_bnd, nb, escale, cvecs, salt_base=200)
+        # The point chains up to the concat layer depend on the coordinates only, the encoder (FPS, ball query, set
+        # abstraction: a long chain of small, latency-bound launches) on nothing they produce: run the former on a
+        # side stream while the encoder occupies the main one (fork / join, also inside a captured graph).
+        n_pre = next((i for i, L in enumerate(layers) if L.cvec_key is not None or L.escale), len(layers))
+        main = torch.cuda.current_stream()
+        if ctx.side_stream is None:
+            ctx.side_stream = torch.cuda.Stream(device=data.device)
+        side = ctx.side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            z0_int = ops.seed_jet(data, int_ids, ni, c_cols, cj)
+            z0_bnd = ops.seed_jet(data, bnd_ids, nb, c_cols, 1)
+            zs_int = chain_forward(ctx, layers[:n_pre], z0_int, ni, None, None, salt_base=100)
+            zs_bnd = chain_forward(ctx, layers[:n_pre], z0_bnd, nb, None, None, salt_base=200)
+        cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None)
+        main.wait_stream(side)
+        zs_int += chain_forward(ctx, layers[n_pre:], zs_int[-1], ni, escale, cvecs, salt_base=100 + n_pre)[1:]
+        zs_bnd += chain_forward(ctx, layers[n_pre:], zs_bnd[-1], nb, escale, cvecs, salt_base=200 + n_pre)[1:]
 
         coup = None
         if plan['family'] == 'pipn' and laplacian == 'reference' and getattr(model, 'coupling', True):

@@ -135,7 +135,7 @@ def end_step() -> None:
 def _weight_block(w: Tensor, col_lo: int, k: int, n: int):
     if k < 8 or (w.stride(0) % 4 == 0 and col_lo % 4 == 0 and w.data_ptr() % 16 == 0):
         return w.data_ptr() + 4 * col_lo, w.stride(0)
-    key = (w.data_ptr(), col_lo, k, n)
+    key = (w.data_ptr(), col_lo, k, n, _stream())     # per stream: the copy is ordered with its consumers
     buf = _WPAD.get(key)
     if buf is None:
         buf = torch.zeros((n, round4(k)), dtype=torch.float32, device=w.device)
