@@ -63,6 +63,7 @@ class StepContext:
 
     def __init__(self, device):
         self.device = device
+        self.side_stream = None
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.training = False
@@ -72,6 +73,8 @@ class StepContext:
 
     def need_workspace(self, nbytes: int):
         if self.workspace.numel() < nbytes:
+            if self.side_stream is not None:      # dW kernels on the side stream may still read the old buffer
+                self.side_stream.synchronize()
             self.workspace = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
 
     def grad(self, p: Optional[nn.Parameter]) -> Optional[Tensor]:
@@ -98,7 +101,12 @@ def chain_forward(ctx: StepContext, layers, z0: Jet, rows_per_geom: int, escale:
 
 def chain_backward(ctx: StepContext, layers, zs, gz: Jet, rows_per_geom: int, escale: Optional[Tensor] = None,
                    gescale: Optional[Tensor] = None, gcvecs: Optional[dict] = None, need_input_grad: bool = False,
-                   salt_base: int = 0) -> Optional[Jet]:
+                   salt_base: int = 0, side: Optional[torch.cuda.Stream] = None) -> Optional[Jet]:
+    """Reverse pass of a chain.  With `side`, the weight-gradient work of every layer (dW kernel + its small,
+    latency-bound finish kernel) is issued on that stream while the main stream goes on with dX: the two big
+    kernels still share the SMs one after the other, but the finish kernels no longer sit on the critical path.
+    The caller joins the streams (and owns the ordering of `ctx.workspace`, which the dW calls share)."""
+    main = torch.cuda.current_stream()
     for i in range(len(layers) - 1, -1, -1):
         L = layers[i]
         zin = zs[i]
@@ -107,8 +115,15 @@ def chain_backward(ctx: StepContext, layers, zs, gz: Jet, rows_per_geom: int, es
         ctx.need_workspace(nbytes)
         gbias = ctx.grad(L.bias) if L.cvec_key is None else None
         gcvec = gcvecs[L.cvec_key] if L.cvec_key is not None else None
-        ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
-                              ctx.workspace)
+        if side is not None:
+            side.wait_stream(main)
+            gz.t.record_stream(side)
+            with torch.cuda.stream(side):
+                ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
+                                      ctx.workspace)
+        else:
+            ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
+                                  ctx.workspace)
         if i > 0 or need_input_grad:
             gz = ops.jet_linear_bwd_dx(gz, L.weight, L.col_lo, zin, tin, gescale if L.escale else None, rows_per_geom,
                                        L.k, L.n)
@@ -557,8 +572,13 @@ class PinnExecutor:
         if escale is not None:
             gescale = torch.empty_like(escale)
             ops.zero_(gescale)
-        chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100)
-        chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200)
+        # the weight-gradient kernels of the two point chains go to the side stream (see chain_backward); the vanilla-PIPN
+        # coupling pass shares the workspace with them, so it keeps everything on one stream
+        wside = ctx.side_stream if coup is None else None
+        chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100, side=wside)
+        chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200, side=wside)
+        if wside is not None:
+            torch.cuda.current_stream().wait_stream(wside)
         if coup is not None:
             from . import coupling
             coupling.backward(self, coup, data, int_ids, zs_int, gy_int, saved, gcvecs)
