@@ -182,12 +182,12 @@ def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int,
     return g, saved
 
 
-def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg: int) -> None:
+def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg: int, side=None) -> None:
     b, n, e = saved['b'], saved['g_n'], saved['e']
     zs = saved['g_zs']
     gz = ops.segmax_bwd(gg, ldgg, saved['g_arg'], zs[-1].t[0], stack.act, b, n, e)
     need = len(stack.levels) > 0
-    gin = chain_backward(ctx, stack.global_layers, zs, Jet(gz, e), n, need_input_grad=need)
+    gin = chain_backward(ctx, stack.global_layers, zs, Jet(gz, e), n, need_input_grad=need, side=side)
     if not need:
         return
     gx, ldgx = gin.t[0], gin.ld
@@ -196,7 +196,7 @@ def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg:
         m_total = sv['slots'].shape[0]
         zs = sv['zs']
         gz = ops.segmax_bwd(gx, ldgx, sv['arg'], zs[-1].t[0], lvl.act, m_total, sv['slots'].shape[1], sv['c'])
-        gein = chain_backward(ctx, lvl.layers, zs, Jet(gz, sv['c']), 0, need_input_grad=(li > 0))
+        gein = chain_backward(ctx, lvl.layers, zs, Jet(gz, sv['c']), 0, need_input_grad=(li > 0), side=side)
         if li > 0:
             gprev = torch.empty((b * sv['n'], sv['ldx']), dtype=torch.float32, device=gx.device)
             ops.zero_(gprev)
@@ -311,7 +311,8 @@ class PinnExecutor:
 
     def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False):
         gz = ops.segmax_bwd(gout, ldgout, sv['arg'], sv['zs'][-1].t[0], sv['act'], sv['n_seg'], sv['seg_len'], sv['c'])
-        return chain_backward(ctx, layers, sv['zs'], Jet(gz, sv['c']), sv['seg_len'], need_input_grad=need_input_grad)
+        return chain_backward(ctx, layers, sv['zs'], Jet(gz, sv['c']), sv['seg_len'], need_input_grad=need_input_grad,
+                              side=ctx.side_stream)
 
     # ---- encode: per-geometry constants ------------------------------------------------------
     def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor]):
@@ -420,7 +421,7 @@ class PinnExecutor:
         gg = ops.jet_linear_bwd_dx(gcv, cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
         fam = plan['family']
         if fam in ('pipn_pp', 'pigano_pp'):
-            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld)
+            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld, side=ctx.side_stream)
         elif fam == 'pigano':
             self._segmax_features_bwd(ctx, plan['geom_layers'], saved['geom'], gg.t[0], gg.ld)
         elif fam == 'pipn':
@@ -430,9 +431,11 @@ class PinnExecutor:
             # gradient of the local features: first lw columns of the concat input, pending activation is
             # applied by the global MLP's first layer (act_cols = lw), so gin[:, :lw] is d/d z_local
             glocal = Jet(gin.t[:, :, :], sv['lw'])
-            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows)
+            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows, side=ctx.side_stream)
         if fam in ('pigano', 'pigano_pp'):
             self._segmax_features_bwd(ctx, plan['branch_layers'], saved['branch'], gescale, gescale.stride(0))
+        if ctx.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(ctx.side_stream)
 
     # ---- public entry points -----------------------------------------------------------------
     def forward_values(self, points: Tensor, data: Tensor, labels: dict, domain: dict) -> Tensor:
