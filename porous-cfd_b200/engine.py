@@ -541,8 +541,12 @@ class PinnExecutor:
             zs_bnd = chain_forward(ctx, layers[:n_pre], z0_bnd, nb, None, None, salt_base=200)
         cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None)
         main.wait_stream(side)
+        # the boundary chain (value only, small grids) fills the gaps of the internal chain from the side stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            zs_bnd += chain_forward(ctx, layers[n_pre:], zs_bnd[-1], nb, escale, cvecs, salt_base=200 + n_pre)[1:]
         zs_int += chain_forward(ctx, layers[n_pre:], zs_int[-1], ni, escale, cvecs, salt_base=100 + n_pre)[1:]
-        zs_bnd += chain_forward(ctx, layers[n_pre:], zs_bnd[-1], nb, escale, cvecs, salt_base=200 + n_pre)[1:]
+        main.wait_stream(side)
 
         coup = None
         if plan['family'] == 'pipn' and laplacian == 'reference' and getattr(model, 'coupling', True):
