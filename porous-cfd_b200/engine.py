@@ -64,6 +64,7 @@ class StepContext:
     def __init__(self, device):
         self.device = device
         self.side_stream = None
+        self.overlap = True      # fork independent work to a side stream (off: one stream, for per-kernel timing)
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.training = False
@@ -312,7 +313,7 @@ class PinnExecutor:
     def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False):
         gz = ops.segmax_bwd(gout, ldgout, sv['arg'], sv['zs'][-1].t[0], sv['act'], sv['n_seg'], sv['seg_len'], sv['c'])
         return chain_backward(ctx, layers, sv['zs'], Jet(gz, sv['c']), sv['seg_len'], need_input_grad=need_input_grad,
-                              side=ctx.side_stream)
+                              side=ctx.side_stream if ctx.overlap else None)
 
     # ---- encode: per-geometry constants ------------------------------------------------------
     def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor]):
@@ -421,7 +422,7 @@ class PinnExecutor:
         gg = ops.jet_linear_bwd_dx(gcv, cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
         fam = plan['family']
         if fam in ('pipn_pp', 'pigano_pp'):
-            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld, side=ctx.side_stream)
+            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld, side=ctx.side_stream if ctx.overlap else None)
         elif fam == 'pigano':
             self._segmax_features_bwd(ctx, plan['geom_layers'], saved['geom'], gg.t[0], gg.ld)
         elif fam == 'pipn':
@@ -431,7 +432,8 @@ class PinnExecutor:
             # gradient of the local features: first lw columns of the concat input, pending activation is
             # applied by the global MLP's first layer (act_cols = lw), so gin[:, :lw] is d/d z_local
             glocal = Jet(gin.t[:, :, :], sv['lw'])
-            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows, side=ctx.side_stream)
+            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows,
+                           side=ctx.side_stream if ctx.overlap else None)
         if fam in ('pigano', 'pigano_pp'):
             self._segmax_features_bwd(ctx, plan['branch_layers'], saved['branch'], gescale, gescale.stride(0))
         if ctx.side_stream is not None:
@@ -532,7 +534,7 @@ class PinnExecutor:
         main = torch.cuda.current_stream()
         if ctx.side_stream is None:
             ctx.side_stream = torch.cuda.Stream(device=data.device)
-        side = ctx.side_stream
+        side = ctx.side_stream if ctx.overlap else main
         side.wait_stream(main)
         with torch.cuda.stream(side):
             z0_int = ops.seed_jet(data, int_ids, ni, c_cols, cj)
@@ -581,7 +583,7 @@ class PinnExecutor:
             ops.zero_(gescale)
         # the weight-gradient kernels of the two point chains go to the side stream (see chain_backward); the vanilla-PIPN
         # coupling pass shares the workspace with them, so it keeps everything on one stream
-        wside = ctx.side_stream if coup is None else None
+        wside = ctx.side_stream if (coup is None and ctx.overlap) else None
         chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100, side=wside)
         chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200, side=wside)
         if wside is not None:
