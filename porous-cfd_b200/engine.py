@@ -18,6 +18,7 @@ Structure of a step:
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -64,7 +65,8 @@ class StepContext:
     def __init__(self, device):
         self.device = device
         self.side_stream = None
-        self.overlap = True      # fork independent work to a side stream (off: one stream, for per-kernel timing)
+        # fork independent work to a side stream (off: one stream, for per-kernel timing / ordered ncu launch lists)
+        self.overlap = os.environ.get('PCFD_NO_OVERLAP', '0') != '1'
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.training = False
