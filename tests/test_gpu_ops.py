@@ -189,6 +189,14 @@ CASES = [  # cj, dims, order, rows, rows_per_geom, k, n, act, use_escale, use_cv
     (1, 0, 0, 4100, 0, 131, 128, 'silu', False, False),
     (4, 3, 1, 3000, 1500, 128, 4, 'silu', False, False),
     (3, 2, 1, 2048, 1024, 10, 64, None, False, False),
+    # shapes served by the thin / small-rows kernels (jet_linear_thin.cu)
+    (1, 0, 0, 32, 0, 1024, 384, None, False, False),      # per-geometry constant of the concat layer: rows = B
+    (1, 0, 0, 20, 0, 100, 50, None, False, False),
+    (1, 0, 0, 5000, 2500, 128, 4, 'silu', False, False),  # last layer, value only
+    (4, 3, 1, 4096, 1024, 352, 3, 'silu', True, False),   # last layer behind a neural operator (branch scaling)
+    (4, 3, 1, 4096, 2048, 3, 64, None, False, False),     # first layer, k = D
+    (1, 0, 0, 6000, 0, 7, 64, None, False, False),        # first layer of a value-only encoder
+    (5, 2, 2, 3000, 1500, 128, 8, 'tanh', False, True),
 ]
 
 
