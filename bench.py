@@ -287,7 +287,6 @@ def main():
     params = list(model.parameters())
     for p in params:
         p.grad = None
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
 
     # The call a user makes: model.training_step(batch) + loss.backward() + optimizer.step() (+ float(loss)), with
     # model.cuda_graph = True (the fused step replays from a CUDA graph) and the NEXT step's pinned-host -> device
@@ -314,14 +313,14 @@ def main():
             v.record_stream(cur)
         pending['next'] = prefetch(i + 1)
         loss = model.training_step(batch, i)
-        opt.zero_grad(set_to_none=True)
+        for p in params:
+            p.grad = None
         loss.backward()
-        if world > 1:     # the parameter gradients are views of one flat buffer: a single NCCL all-reduce
-            flat = model.executor.last_flat_grad
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
-        opt.step()
-        return float(loss.detach())      # device -> host read of the step's result
+        flat = model.executor.last_flat_grad      # every p.grad is a view of this buffer
+        if world > 1:
+            dist.all_reduce(flat)                 # one NCCL all-reduce; 1/world is folded into the Adam kernel
+        trainer.step(flat)                        # fused Adam on the flat parameter buffer (one launch)
+        return float(loss.detach())               # device -> host read of the step's result
 
     for i in range(W):
         e2e_step(i)
@@ -421,7 +420,7 @@ def main():
             'loss': loss_value, 'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'ms_per_step': ms_e2e / K, 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); '
-                           'Adam.step(); float(loss)  [next batch prefetched on a copy stream]'},
+                           'FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]'},
             'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line))
     if world > 1:

@@ -83,10 +83,13 @@ class FlatAdamTrainer:
         if self.world > 1:
             dist.all_reduce(self.model.executor.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
 
-    def step(self):
-        """Adam (torch.optim.Adam semantics) on the flat buffers; 1/world of the all-reduce is folded in."""
+    def step(self, grad: Optional[torch.Tensor] = None):
+        """Adam (torch.optim.Adam semantics) on the flat buffers, one kernel; 1/world of the all-reduce is folded in.
+        `grad`: a flat gradient other than the executor's own buffer (after `loss.backward()` through the autograd
+        seam that is `model.executor.last_flat_grad`, of which every `p.grad` is a view)."""
         from .. import ops
-        ops.adam_step(self.flat_param, self.model.executor.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_dev,
+        g = self.model.executor.flat_grad if grad is None else grad
+        ops.adam_step(self.flat_param, g, self.exp_avg, self.exp_avg_sq, self.step_dev,
                       self.lr_dev, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
 
     def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
