@@ -1,7 +1,7 @@
 // Jet layers whose shape makes a tensor-core tile pointless (fp32 FFMA, exact):
 //
 //   thin_n   n <= 8 outputs     (the last layer of every point chain: Linear(128, D+1), Linear(352, 3), ...):
-//            forward = CJ*n dot products per row, one warp per row; dX = a rank-n update per row followed by the
+//            forward = CJ*n dot products per row, 8 lanes per row; dX = a rank-n update per row followed by the
 //            reverse activation jet -- both HBM-bound streams over the wide operand.
 //   thin_k   k <= 16 inputs     (the first layer of every chain: Linear(D, 64), the value-only encoders' first
 //            layers): forward = k FMAs per output, HBM-bound on the output.
@@ -46,22 +46,28 @@ __global__ void __launch_bounds__(256) thin_n_fwd_kernel(ThinFwdArgs a) {
     wsm[i] = (j < a.n && kk < a.k) ? __ldg(a.w + (int64_t)j * a.ldw + kk) : 0.0f;
   }
   __syncthreads();
+  // 8 lanes per row (4 rows per warp): 3 shuffle steps per accumulator instead of 5, and exactly n <= 8 writer lanes
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, rg = lane >> 3;
   const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
   const bool plain = a.tin.act == PCFD_ACT_NONE && a.tin.escale == nullptr && a.tin.drop_p == 0.0f;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < a.rows; row += (int64_t)gridDim.x * 8) {
+  for (int64_t row0 = ((int64_t)blockIdx.x * 8 + warp) * 4; row0 < a.rows; row0 += (int64_t)gridDim.x * 32) {
+    const int64_t row = row0 + rg;
+    const bool valid = row < a.rows;
     float acc[CJ][8];
 #pragma unroll
     for (int c = 0; c < CJ; ++c)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[c][j] = 0.0f;
-    const int64_t geom = geom_of(row, a.rows_per_geom);
-    for (int col0 = lane * 4; col0 < a.k; col0 += 128) {
+    const int64_t geom = valid ? geom_of(row, a.rows_per_geom) : 0;
+    for (int col0 = sub * 4; col0 < a.k; col0 += 32) {
       float v[CJ][4];
 #pragma unroll
       for (int c = 0; c < CJ; ++c) {
         const float* p = a.zin + c * a.zin_ps + row * a.ldzin + col0;
-        if (a.vec_in && col0 + 4 <= a.k) {
+        if (!valid) {
+          v[c][0] = v[c][1] = v[c][2] = v[c][3] = 0.0f;
+        } else if (a.vec_in && col0 + 4 <= a.k) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(p));
           v[c][0] = x.x; v[c][1] = x.y; v[c][2] = x.z; v[c][3] = x.w;
         } else {
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(256) thin_n_fwd_kernel(ThinFwdArgs a) {
           for (int e = 0; e < 4; ++e) v[c][e] = col0 + e < a.k ? __ldg(p + e) : 0.0f;
         }
       }
-      if (!plain) {
+      if (!plain && valid) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (col0 + e < a.tin.act_cols) {
@@ -100,23 +106,24 @@ __global__ void __launch_bounds__(256) thin_n_fwd_kernel(ThinFwdArgs a) {
 #pragma unroll
         for (int c = 0; c < CJ; ++c) {
           float t = acc[c][j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          t += __shfl_xor_sync(0xffffffffu, t, 1);
+          t += __shfl_xor_sync(0xffffffffu, t, 2);
+          t += __shfl_xor_sync(0xffffffffu, t, 4);
           acc[c][j] = t;
         }
       }
     }
-    if (lane < a.n) {
+    if (valid && sub < a.n) {
 #pragma unroll
       for (int c = 0; c < CJ; ++c) {
         float val = acc[c][0];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) val = lane == j ? acc[c][j] : val;
+        for (int j = 1; j < 8; ++j) val = sub == j ? acc[c][j] : val;
         if (c == 0) {
-          if (a.bias != nullptr) val += __ldg(a.bias + lane);
-          if (a.cvec != nullptr) val += __ldg(a.cvec + geom * a.ldcvec + lane);
+          if (a.bias != nullptr) val += __ldg(a.bias + sub);
+          if (a.cvec != nullptr) val += __ldg(a.cvec + geom * a.ldcvec + sub);
         }
-        a.zout[c * a.zout_ps + row * a.ldzout + lane] = val;
+        a.zout[c * a.zout_ps + row * a.ldzout + sub] = val;
       }
     }
   }
@@ -366,7 +373,7 @@ extern "C" int pcfd_thin_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_
   a.vec_out = al16(zout) && ldzout % 4 == 0 && (cj == 1 || zout_ps % 4 == 0);
   if (kind == 0) {
     const int smem = 8 * ((k + 3) & ~3) * 4;
-    const int grid = grid_for(rows, 8);
+    const int grid = grid_for(rows, 32);
 #define PCFD_THIN(CJ_) thin_n_fwd_kernel<CJ_><<<grid, 256, smem, st>>>(a); break;
     switch (cj) { case 1: PCFD_THIN(1) case 3: PCFD_THIN(3) case 4: PCFD_THIN(4) case 5: PCFD_THIN(5) case 7: PCFD_THIN(7) }
 #undef PCFD_THIN

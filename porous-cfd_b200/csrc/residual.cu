@@ -250,24 +250,20 @@ struct FinishArgs {
 };
 
 __global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
-  __shared__ double red[256];
   __shared__ double tot[3 * NSLOT];
-  const int tid = threadIdx.x;
-  for (int q = 0; q < 3 * NSLOT; ++q) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // one warp per (region, slot) sum, three rounds of eight: fixed order -> deterministic
+  for (int q = warp; q < 3 * NSLOT; q += 8) {
     const int region = q / NSLOT, slot = q % NSLOT;
     const float* p = region == 0 ? a.p_int : (region == 1 ? a.p_bnd : a.p_obs);
     const int nb = region == 0 ? a.b_int : (region == 1 ? a.b_bnd : a.b_obs);
     double s = 0.0;
-    for (int b = tid; b < nb; b += 256) s += (double)p[(int64_t)b * NSLOT + slot];
-    red[tid] = s;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (tid < o) red[tid] += red[tid + o];
-      __syncthreads();
-    }
-    if (tid == 0) tot[q] = red[0];
-    __syncthreads();
+    for (int b = lane; b < nb; b += 32) s += (double)p[(int64_t)b * NSLOT + slot];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tot[q] = s;
   }
+  __syncthreads();
   if (tid == 0) {
     const int D = a.dims;
     float* out = a.out;
