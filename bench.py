@@ -192,6 +192,8 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") and any NCCL_DEBUG output go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=device)
     W, K = max(3, args.warmup), max(1, args.steps)
     if args.engine is not None:
