@@ -148,10 +148,29 @@ def run_reference(args):
                              'sample': f'{n_geom} geometries x {SHAPE["n_internal"]} collocation points per step, {steps} steps'},
             'e2e': {'value': pts, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write there too (NCCL prints its version banner with
+    NCCL_DEBUG=VERSION, which this image sets), so file descriptor 1 is pointed at stderr for the whole process and the
+    result line goes to a duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + '\n').encode())
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -192,8 +211,6 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") and any NCCL_DEBUG output go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=device)
     W, K = max(3, args.warmup), max(1, args.steps)
     if args.engine is not None:
@@ -424,7 +441,7 @@ def main():
                     'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); '
                            'FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]'},
             'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
