@@ -362,7 +362,12 @@ static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n)
   const int passes = p.passes_n * p.passes_k;
   int64_t splits = num_sms() / passes;
   if (splits < 1) splits = 1;
-  const int64_t min_rows = 8 * (int64_t)p.r;                       // a few ring iterations per CTA
+  // at least a few ring iterations per CTA.  Measured (PCFD_DW_MIN_ITERS = 2..64 on the abc layers): a CTA's pipeline is
+  // latency-bound, so more, shorter splits win over fewer partials -- 8 and below are equal, 32 costs 20-50 % on the
+  // small layers
+  static int min_iters = -1;
+  if (min_iters < 0) { const char* e = getenv("PCFD_DW_MIN_ITERS"); min_iters = e ? atoi(e) : 8; }
+  const int64_t min_rows = (int64_t)min_iters * p.r;
   const int64_t max_splits = (rows + min_rows - 1) / min_rows;
   if (splits > max_splits) splits = max_splits;
   int64_t rps = (rows + splits - 1) / splits;
