@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpcfd_sm100.so')
+LIB_PATH = os.environ.get('PCFD_LIB_PATH') or os.path.join(HERE, 'libpcfd_sm100.so')   # override: experiments with variant builds
 
 ACT_NONE, ACT_SILU, ACT_TANH = 0, 1, 2
 ACT_CODES = {None: ACT_NONE, 'none': ACT_NONE, 'silu': ACT_SILU, 'tanh': ACT_TANH}

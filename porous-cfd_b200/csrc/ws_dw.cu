@@ -28,8 +28,11 @@
 namespace pcfd {
 namespace ws {
 
-constexpr int DW_GROUPS = 4, DW_GROUP = 128;
-constexpr int DW_W_TMA = DW_GROUPS * DW_GROUP / 32, DW_W_MMA = DW_W_TMA + 1, DW_W_SUM = DW_W_TMA + 2;
+#ifndef PCFD_DW_MAX_GROUPS
+#define PCFD_DW_MAX_GROUPS 4
+#endif
+constexpr int DW_XF_THREADS = 512;      // transform threads (16 warps), split into a.groups groups at run time
+constexpr int DW_W_TMA = DW_XF_THREADS / 32, DW_W_MMA = DW_W_TMA + 1, DW_W_SUM = DW_W_TMA + 2;
 constexpr int DW_THREADS = (DW_W_SUM + 1) * 32;
 constexpr int DW_MAX_STAGES = 8;
 constexpr int DW_SMEM_MAX = 232448 - 2048;      // dynamic shared memory we may ask for (227 KB less static + alignment slack)
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < STG; ++s) {
       tc::mbar_init(&raw_full[s], 1);
-      tc::mbar_init(&ops_ready[s], DW_GROUP + (a.colsum != nullptr ? 32 : 0));
+      tc::mbar_init(&ops_ready[s], (16 / a.groups) * 32 + (a.colsum != nullptr ? 32 : 0));
       tc::mbar_init(&stage_free[s], 1);
     }
     tc::mbar_init(&acc_full, 1);
@@ -187,8 +190,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
     }
   } else {
     // ================================ transform ================================
-    const int g = warp >> 2;
-    const int tt = tid - g * DW_GROUP;
+    const int gs = (16 / a.groups) * 32;              // threads of one transform group (whole warps)
+    const int g = warp / (gs >> 5);
+    const int tt = tid - g * gs;
     const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
     const uint32_t hseed = dropout_seed_hash(seed, a.tin.salt);
     const bool scaled = a.tin.escale != nullptr || a.tin.drop_p > 0.0f;
@@ -203,35 +207,35 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
       const int64_t row0 = r_begin + (int64_t)it * R;
       tc::bounded_wait(&raw_full[s], ph);
       // ---- A: remainder tile of gzout (same swizzled position in the lo tile)
-      for (int i0 = tt; i0 < a_chunks; i0 += 4 * DW_GROUP) {
+      for (int i0 = tt; i0 < a_chunks; i0 += 4 * gs) {
         float4 x[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (i0 + q * DW_GROUP < a_chunks) x[q] = *reinterpret_cast<const float4*>(st + (size_t)(i0 + q * DW_GROUP) * 16);
+          if (i0 + q * gs < a_chunks) x[q] = *reinterpret_cast<const float4*>(st + (size_t)(i0 + q * gs) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (i0 + q * DW_GROUP < a_chunks)
-            *reinterpret_cast<float4*>(st + A_LO + (size_t)(i0 + q * DW_GROUP) * 16) =
+          if (i0 + q * gs < a_chunks)
+            *reinterpret_cast<float4*>(st + A_LO + (size_t)(i0 + q * gs) * 16) =
                 make_float4(x[q].x - trunc_tf32(x[q].x), x[q].y - trunc_tf32(x[q].y), x[q].z - trunc_tf32(x[q].z),
                             x[q].w - trunc_tf32(x[q].w));
       }
       uint8_t* bt = st + B_HI;
       if (plain) {
-        for (int i0 = tt; i0 < b_chunks; i0 += 4 * DW_GROUP) {
+        for (int i0 = tt; i0 < b_chunks; i0 += 4 * gs) {
           float4 x[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (i0 + q * DW_GROUP < b_chunks) x[q] = *reinterpret_cast<const float4*>(bt + (size_t)(i0 + q * DW_GROUP) * 16);
+            if (i0 + q * gs < b_chunks) x[q] = *reinterpret_cast<const float4*>(bt + (size_t)(i0 + q * gs) * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            if (i0 + q * DW_GROUP < b_chunks)
-              *reinterpret_cast<float4*>(bt + (B_LO - B_HI) + (size_t)(i0 + q * DW_GROUP) * 16) =
+            if (i0 + q * gs < b_chunks)
+              *reinterpret_cast<float4*>(bt + (B_LO - B_HI) + (size_t)(i0 + q * gs) * 16) =
                   make_float4(x[q].x - trunc_tf32(x[q].x), x[q].y - trunc_tf32(x[q].y), x[q].z - trunc_tf32(x[q].z),
                               x[q].w - trunc_tf32(x[q].w));
         }
       } else {
         // ---- B: activation jet in place + remainder tile
-        for (int idx = tt; idx < b_items; idx += DW_GROUP) {
+        for (int idx = tt; idx < b_items; idx += gs) {
           const int j = idx & 7, r = (idx >> 3) & (R - 1), blk = idx / (8 * R);
           uint8_t* base = bt + blk * BLK + r * 128 + ((((uint32_t)(j >> 1) ^ (uint32_t)(r & 3)) << 5) | ((uint32_t)(j & 1) << 4));
           float v[CJ][4];
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
       tc::tc_fence_after();
     }
 #pragma unroll 1
-    for (int cbi = cgrp; cbi < total_cb; cbi += DW_GROUPS) {
+    for (int cbi = cgrp; cbi < total_cb; cbi += 4) {
       const int mt = cbi / blocks_per_mt;
       const int kl = (cbi - mt * blocks_per_mt) * 32;
       const int nn = n0 + mt * 128 + 32 * q + lane;
@@ -325,6 +329,10 @@ static inline void dw_ring(int fit, int* stages, int* groups) {
   else if (fit >= 6) { *stages = 6; *groups = 3; }
   else if (fit >= 4) { *stages = 4; *groups = 4; }
   else { *stages = fit; *groups = fit; }
+  // With a short ring the time a stage spends in the transform is on the critical path: fewer, larger groups (measured:
+  // 1 group of 16 warps at 3 stages 154 -> 141 us on the 384->128 layer); with 6-8 small stages 3-4 groups are better.
+  if (*stages <= 4) *groups = (*stages % 2 == 0) ? 2 : 1;
+  while (*groups > PCFD_DW_MAX_GROUPS || (*groups > 0 && *stages % *groups != 0)) --*groups;
 }
 
 static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n) {

@@ -27,8 +27,13 @@
 namespace pcfd {
 namespace ws {
 
-constexpr int GROUP = 128;             // threads of one transform group
-constexpr int W_TMA = STAGES * GROUP / 32, W_MMA = W_TMA + 1, W_EPI = W_TMA + 2;
+#ifndef PCFD_FWD_GROUPS
+#define PCFD_FWD_GROUPS 2
+#endif
+constexpr int NGROUPS = PCFD_FWD_GROUPS;   // transform groups; group g takes ring iterations g, g + NGROUPS, ... (NGROUPS divides STAGES)
+constexpr int GROUP = 512 / NGROUPS;       // threads of one transform group
+constexpr int W_TMA = 16, W_MMA = W_TMA + 1, W_EPI = W_TMA + 2;
+static_assert(STAGES % NGROUPS == 0, "a group must see every use of its stages");
 constexpr int THREADS = (W_EPI + 8) * 32;
 
 struct FwdArgs {
@@ -147,26 +152,26 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
     }
   } else if (warp < W_TMA) {
     // ================================ transform ================================
-    const int g = warp >> 2;                                  // group = ring stage it owns
+    const int g = warp / (GROUP / 32);
     const int tt = tid - g * GROUP;
     const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
     const uint32_t hseed = dropout_seed_hash(seed, a.tin.salt);
     const bool scaled = a.tin.escale != nullptr || a.tin.drop_p > 0.0f;
     const bool plain = a.tin.act == PCFD_ACT_NONE && !scaled;
     constexpr int A_ITEMS = POINTS * 4;                       // (point, 16-byte chunk) positions, all channels each
-    constexpr int A_PER = A_ITEMS / GROUP;
-    constexpr int B_PER = NT * 4 / GROUP;
-    static_assert(A_ITEMS % GROUP == 0 && (NT * 4) % GROUP == 0, "work must divide over the group");
-    uint8_t* st = smem + g * STAGE_BYTES;
-    uint8_t* bt = st + 2 * A_BYTES;
+    constexpr int A_PER = (A_ITEMS + GROUP - 1) / GROUP;
+    constexpr int B_PER = (NT * 4 + GROUP - 1) / GROUP;
     const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)nkc;
-    for (uint32_t it = g; it < n_it; it += STAGES) {
+    for (uint32_t it = g; it < n_it; it += NGROUPS) {
+      const int sidx = (int)(it % STAGES);
+      uint8_t* st = smem + sidx * STAGE_BYTES;
+      uint8_t* bt = st + 2 * A_BYTES;
       const uint32_t tl = it / (uint32_t)nkc;
       const int kc = (int)(it - tl * (uint32_t)nkc);
       const int t = (int)blockIdx.x + (int)tl * (int)gridDim.x;
       const int64_t row0 = (int64_t)(t / a.n_passes) * POINTS;
       const uint32_t ph = (it / STAGES) & 1;
-      tc::bounded_wait(&raw_full[g], ph);
+      tc::bounded_wait(&raw_full[sidx], ph);
       if (!(a.dbg & 1)) {
         // ---- B: remainder tile of the weights
         {
@@ -174,11 +179,12 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
 #pragma unroll
           for (int q = 0; q < B_PER; ++q) {
             const int item = tt + q * GROUP;
-            wv[q] = *reinterpret_cast<const float4*>(bt + swz<64>(item >> 2, item & 3));
+            if (item < NT * 4) wv[q] = *reinterpret_cast<const float4*>(bt + swz<64>(item >> 2, item & 3));
           }
 #pragma unroll
           for (int q = 0; q < B_PER; ++q) {
             const int item = tt + q * GROUP;
+            if (item >= NT * 4) continue;
             const float4 x = wv[q];
             *reinterpret_cast<float4*>(bt + B_BYTES + swz<64>(item >> 2, item & 3)) =
                 make_float4(x.x - trunc_tf32(x.x), x.y - trunc_tf32(x.y), x.z - trunc_tf32(x.z), x.w - trunc_tf32(x.w));
@@ -188,6 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
 #pragma unroll
         for (int q = 0; q < A_PER; ++q) {
           const int item = tt + q * GROUP;
+          if (item >= A_ITEMS) continue;
           const int point = item >> 2, j = item & 3;
           uint8_t* base = st + (point >> 5) * CJ * SLAB_BYTES + swz<64>(point & 31, j);
           float v[CJ][4];
@@ -213,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
         }
       }
       tc::fence_proxy_async();
-      mbar_arrive(&ops_ready[g]);
+      mbar_arrive(&ops_ready[sidx]);
     }
   } else {
     // ================================ epilogue (warps W_EPI .. W_EPI+7) ================================
