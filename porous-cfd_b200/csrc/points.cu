@@ -2,6 +2,8 @@
 // gather / scatter) and the FoamData gathers.  Index results are bit-exact against
 // oracle/pyg_restate.py: squared distances use separately rounded fp32 multiplies and adds in
 // coordinate order (no FMA contraction), ties resolve to the lowest index.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pcfd {
@@ -110,12 +112,16 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(const float* __restrict__
     }
     const unsigned wd = __reduce_max_sync(0xffffffffu, bd);
     const unsigned wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
-    if (lane == 0) { slot_d[s & 1][warp] = wd; slot_i[s & 1][warp] = wi; }
-    __syncthreads();
-    unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
-    unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
-    const unsigned gd = __reduce_max_sync(0xffffffffu, vd);
-    cur = (int)__reduce_min_sync(0xffffffffu, vd == gd ? vi : 0xffffffffu);
+    if (MAXT == 32) {             // a single warp holds the whole geometry: no barrier, no exchange through shared memory
+      cur = (int)wi;
+    } else {
+      if (lane == 0) { slot_d[s & 1][warp] = wd; slot_i[s & 1][warp] = wi; }
+      __syncthreads();
+      unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
+      unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
+      const unsigned gd = __reduce_max_sync(0xffffffffu, vd);
+      cur = (int)__reduce_min_sync(0xffffffffu, vd == gd ? vi : 0xffffffffu);
+    }
     if (tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + cur;
   }
 }
@@ -298,9 +304,15 @@ extern "C" int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   if (n <= 8192) {
-    // 8 or 16 points per thread (measured: 32 per thread is slower at n = 8192)
     const size_t rsmem = (size_t)n * dims * sizeof(float);
-    const int ppt = n <= 1024 ? 8 : (n <= 4096 ? 16 : 8);
+    // points per thread: as few as the 1024-thread limit allows, but 2 rather than 1 (measured at n = 1000, 32 geometries:
+    // 1 -> 0.152 ms, 2 -> 0.135, 4 -> 0.204, 8 -> 0.292, 16 -> 0.577, one warp with 32 -> 0.333: the per-thread update /
+    // compare chain, not the block barrier, is the critical path of a sample)
+    static int force_ppt = -1;
+    if (force_ppt < 0) { const char* ev = getenv("PCFD_FPS_PPT"); force_ppt = ev ? atoi(ev) : 0; }
+    int ppt = n <= 2048 ? 2 : (n <= 4096 ? 4 : 8);
+    if ((force_ppt == 1 || force_ppt == 2 || force_ppt == 4 || force_ppt == 8 || force_ppt == 16) && n <= 1024 * force_ppt)
+      ppt = force_ppt;
     int rthreads = (n + ppt - 1) / ppt;
     rthreads = (rthreads + 31) / 32 * 32;
     if (rthreads < 32) rthreads = 32;
@@ -310,8 +322,29 @@ extern "C" int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t 
       if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;                                                               \
       fps_reg_kernel<D_, P_, 1024><<<n_geom, rthreads, rsmem, st>>>(pos, n, m, idx_out);                                 \
     }
-    if (dims == 2) { if (ppt == 8) PCFD_FPS_REG(2, 8) else PCFD_FPS_REG(2, 16) }
-    else { if (ppt == 8) PCFD_FPS_REG(3, 8) else PCFD_FPS_REG(3, 16) }
+    static int one_warp = -1;     // PCFD_FPS_ONE_WARP=0 disables the single-warp variant (experiments)
+    if (one_warp < 0) { const char* ev = getenv("PCFD_FPS_ONE_WARP"); one_warp = ev ? atoi(ev) : 0; }   // measured slower: 0.33 vs 0.29 ms
+    if (n <= 1024 && one_warp) {
+      // one warp per geometry, 32 points per lane: the per-sample critical path loses the block barrier
+      if (dims == 2) {
+        e = cudaFuncSetAttribute(fps_reg_kernel<2, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+        fps_reg_kernel<2, 32, 32><<<n_geom, 32, rsmem, st>>>(pos, n, m, idx_out);
+      } else {
+        e = cudaFuncSetAttribute(fps_reg_kernel<3, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+        fps_reg_kernel<3, 32, 32><<<n_geom, 32, rsmem, st>>>(pos, n, m, idx_out);
+      }
+      PCFD_CHECK_LAUNCH();
+      return PCFD_OK;
+    }
+    if (dims == 2) {
+      if (ppt == 1) PCFD_FPS_REG(2, 1) else if (ppt == 2) PCFD_FPS_REG(2, 2) else if (ppt == 4) PCFD_FPS_REG(2, 4)
+      else if (ppt == 8) PCFD_FPS_REG(2, 8) else PCFD_FPS_REG(2, 16)
+    } else {
+      if (ppt == 1) PCFD_FPS_REG(3, 1) else if (ppt == 2) PCFD_FPS_REG(3, 2) else if (ppt == 4) PCFD_FPS_REG(3, 4)
+      else if (ppt == 8) PCFD_FPS_REG(3, 8) else PCFD_FPS_REG(3, 16)
+    }
 #undef PCFD_FPS_REG
     PCFD_CHECK_LAUNCH();
     return PCFD_OK;
