@@ -126,6 +126,98 @@ __global__ void __launch_bounds__(MAXT) fps_reg_kernel(const float* __restrict__
   }
 }
 
+// Thread-block-cluster variant for 2048 < n <= 65536: a geometry is spread over the CTAs of one cluster (contiguous
+// index ranges, PPT points per thread in registers).  Per sample every CTA reduces its own range (warp redux + one block
+// barrier), the thread that owns the CTA's best point publishes {distance, index, coordinates} in its CTA's shared
+// memory, ONE cluster barrier later every thread reads the (<= 8) published records of all CTAs through distributed
+// shared memory and picks the winner -- so the per-thread chain stays as short as in the single-CTA kernel while up to
+// 8 SMs work on one geometry.  Same arithmetic and tie rule (largest distance, then lowest index).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_ld_u32(const void* local_smem_ptr, uint32_t cta_rank) {
+  uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr)), raddr, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(raddr) : "memory");
+  return v;
+}
+
+template <int DIMS, int PPT>
+__global__ void __launch_bounds__(1024) fps_cluster_kernel(const float* __restrict__ pos, int n, int m, int csize,
+                                                           int chunk, int64_t* __restrict__ idx_out) {
+  __shared__ unsigned slot_d[2][32], slot_i[2][32];
+  __shared__ unsigned rec[2][2 + DIMS];                 // published record of this CTA: distance bits, index, coordinates
+  const int g = blockIdx.x / csize;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const float* gp = pos + (size_t)g * n * DIMS;
+  const int p_lo = (int)rank * chunk;
+  const int p_hi = min(n, p_lo + chunk);
+  float px[PPT][DIMS], md[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int p = p_lo + tid + i * nt;
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) px[i][d] = p < p_hi ? __ldg(gp + (size_t)p * DIMS + d) : 0.0f;
+    md[i] = p < p_hi ? INFINITY : 0.0f;
+  }
+  float c[DIMS];
+#pragma unroll
+  for (int d = 0; d < DIMS; ++d) c[d] = __ldg(gp + d);        // first sample: point 0
+  if (rank == 0 && tid == 0) idx_out[(size_t)g * m] = (int64_t)g * n;
+  for (int s = 1; s < m; ++s) {
+    unsigned bd = 0u, bi = 0xffffffffu;
+    int bslot = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const float d = fminf(md[i], sqdist<DIMS>(px[i], c));
+      md[i] = d;
+      const unsigned db = __float_as_uint(d);
+      const unsigned p = (unsigned)(p_lo + tid + i * nt);
+      if (p < (unsigned)p_hi && (db > bd || bi == 0xffffffffu)) { bd = db; bi = p; bslot = i; }
+    }
+    const unsigned wd = __reduce_max_sync(0xffffffffu, bd);
+    const unsigned wi = __reduce_min_sync(0xffffffffu, bd == wd ? bi : 0xffffffffu);
+    if (lane == 0) { slot_d[s & 1][warp] = wd; slot_i[s & 1][warp] = wi; }
+    __syncthreads();
+    const unsigned vd = lane < nwarps ? slot_d[s & 1][lane] : 0u;
+    const unsigned vi = lane < nwarps ? slot_i[s & 1][lane] : 0xffffffffu;
+    const unsigned cd = __reduce_max_sync(0xffffffffu, vd);
+    const unsigned cidx = __reduce_min_sync(0xffffffffu, vd == cd ? vi : 0xffffffffu);
+    if (cidx == 0xffffffffu) {                               // a CTA whose range is empty publishes "nothing"
+      if (tid == 0) { rec[s & 1][0] = 0u; rec[s & 1][1] = 0xffffffffu; }
+    } else if (bi == cidx) {                                 // exactly one thread owns that point
+      rec[s & 1][0] = cd;
+      rec[s & 1][1] = cidx;
+#pragma unroll
+      for (int d = 0; d < DIMS; ++d) {
+        float v = px[0][d];
+#pragma unroll
+        for (int i = 1; i < PPT; ++i) v = bslot == i ? px[i][d] : v;
+        rec[s & 1][2 + d] = __float_as_uint(v);
+      }
+    }
+    cluster_sync_all();
+    unsigned gd = 0u, gi = 0xffffffffu;
+    int grank = 0;
+    for (int r = 0; r < csize; ++r) {
+      const unsigned d_r = dsmem_ld_u32(&rec[s & 1][0], (uint32_t)r);
+      const unsigned i_r = dsmem_ld_u32(&rec[s & 1][1], (uint32_t)r);
+      if (i_r != 0xffffffffu && (d_r > gd || gi == 0xffffffffu || (d_r == gd && i_r < gi))) { gd = d_r; gi = i_r; grank = r; }
+    }
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) c[d] = __uint_as_float(dsmem_ld_u32(&rec[s & 1][2 + d], (uint32_t)grank));
+    if (rank == 0 && tid == 0) idx_out[(size_t)g * m + s] = (int64_t)g * n + (int)gi;
+  }
+  cluster_sync_all();       // nobody leaves while a peer may still read its shared memory
+}
+
 // Point sets too large for one SM's shared memory (config 5: up to 64k boundary points per geometry): coordinates
 // are read through L1/L2 and the running min-distances live in a caller-provided scratch array [n_geom][n].
 // Same arithmetic and tie rule as above; ~1 us per sample, one CTA of 1024 threads per geometry.
@@ -287,12 +379,44 @@ using namespace pcfd;
 
 extern "C" size_t pcfd_fps_workspace_bytes(int32_t n_geom, int32_t n, int32_t dims) {
   if (n_geom <= 0 || n <= 0) return 0;
+  // the register / cluster kernels (n <= 65536) need none; the size is reported all the same so that the fall-back
+  // (PCFD_FPS_CLUSTER=0) keeps working with the caller's buffer
   return (size_t)n * (dims + 1) * sizeof(float) > 220 * 1024 ? (size_t)n_geom * n * sizeof(float) : 0;
 }
 
 extern "C" int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
                            void* workspace, size_t workspace_bytes, void* stream) {
   if (!pos || !idx_out || n_geom <= 0 || n <= 0 || m <= 0 || m > n || (dims != 2 && dims != 3)) return PCFD_ERR_ARG;
+  // The cluster kernel is bit-exact (tests run it with PCFD_FPS_CLUSTER=1) but NOT the default: measured on a B200, the
+  // per-sample cluster barrier + distributed-shared-memory reads cost more than the shorter per-thread chain saves
+  // (windbreaks 8192 -> 4096 points, 2 geometries: 8.8 ms against 5.3 ms for one CTA per geometry; 16384 points: 25 vs 18).
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* ev = getenv("PCFD_FPS_CLUSTER"); use_cluster = ev ? atoi(ev) : 0; }
+  if (use_cluster && n > 2048 && n <= 65536) {
+    // cluster size: 2 points per thread while 8 CTAs x 1024 threads suffice, then more points per thread
+    int csize = (n + 2047) / 2048;
+    csize = csize <= 2 ? 2 : (csize <= 4 ? 4 : 8);
+    const int chunk = (n + csize - 1) / csize;
+    const int ppt = chunk <= 2048 ? 2 : (chunk <= 4096 ? 4 : 8);
+    int threads = ((chunk + ppt - 1) / ppt + 31) / 32 * 32;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_geom * csize));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t ce;
+#define PCFD_FPS_CL(D_, P_) ce = cudaLaunchKernelEx(&cfg, fps_cluster_kernel<D_, P_>, pos, (int)n, (int)m, csize, chunk, idx_out)
+    if (dims == 2) { if (ppt == 2) PCFD_FPS_CL(2, 2); else if (ppt == 4) PCFD_FPS_CL(2, 4); else PCFD_FPS_CL(2, 8); }
+    else { if (ppt == 2) PCFD_FPS_CL(3, 2); else if (ppt == 4) PCFD_FPS_CL(3, 4); else PCFD_FPS_CL(3, 8); }
+#undef PCFD_FPS_CL
+    if (ce != cudaSuccess) return PCFD_ERR_CUDA + (int)ce;
+    return PCFD_OK;
+  }
   const size_t smem = (size_t)n * (dims + 1) * sizeof(float);
   if (smem > 220 * 1024) {
     if (workspace == nullptr || workspace_bytes < pcfd_fps_workspace_bytes(n_geom, n, dims)) return PCFD_ERR_WORKSPACE;

@@ -61,6 +61,31 @@ def test_fps_bit_exact_against_oracle(ops, shape):
     assert all(len(set(r.tolist())) == m for r in per) and bool((per[:, 0] == 0).all())
 
 
+@pytest.mark.parametrize('shape', [(2, 4096, 3, 0.25), (1, 8192, 3, 0.5), (2, 20000, 2, 0.02)])
+def test_fps_cluster_kernel_bit_exact(ops, shape):
+    """The thread-block-cluster / distributed-shared-memory variant (opt-in, PCFD_FPS_CLUSTER=1) in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    nb, n, d, ratio = shape
+    code = f'''
+import sys, torch
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import pcfd_import; pcfd_import.load()
+from porous_cfd_b200 import ops
+from oracle import pyg_restate
+g = torch.Generator().manual_seed({n})
+pos = torch.rand({nb}, {n}, {d}, generator=g) * 2 - 1
+want = pyg_restate.fps(pos.reshape(-1, {d}), torch.arange({nb}).repeat_interleave({n}), {ratio})
+got = ops.fps(pos.cuda(), {ratio}).cpu().flatten()
+assert torch.equal(got, want)
+print("cluster fps ok")
+'''
+    env = dict(os.environ, PCFD_FPS_CLUSTER='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'cluster fps ok' in r.stdout, r.stderr[-2000:]
+
+
 def test_fps_ties_pick_lowest_index(ops):
     pos = torch.tensor([[[0., 0.], [1., 0.], [1., 0.], [0., 1.], [0., 1.], [0.5, 0.5]]])
     assert ops.fps(dev(pos), 0.5).cpu().flatten().tolist() == [0, 1, 3]
