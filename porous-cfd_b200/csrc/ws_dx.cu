@@ -24,8 +24,13 @@
 namespace pcfd {
 namespace ws {
 
-constexpr int DX_GROUP = 32;
-constexpr int DX_W_TMA = STAGES * DX_GROUP / 32, DX_W_MMA = DX_W_TMA + 1, DX_W_EPI = DX_W_TMA + 2;
+#ifndef PCFD_DX_GROUPS
+#define PCFD_DX_GROUPS 4
+#endif
+constexpr int DX_NGROUPS = PCFD_DX_GROUPS;       // remainder (lo-split) groups; group g takes ring iterations g, g + NGROUPS, ...
+constexpr int DX_GROUP = 128 / DX_NGROUPS;      // threads per group (4 warps in total)
+constexpr int DX_W_TMA = 4, DX_W_MMA = DX_W_TMA + 1, DX_W_EPI = DX_W_TMA + 2;
+static_assert(STAGES % DX_NGROUPS == 0, "a group must see every use of its stages");
 constexpr int DX_EPI_WARPS = 16, DX_EPI_THREADS = DX_EPI_WARPS * 32;
 constexpr int DX_THREADS = (DX_W_EPI + DX_EPI_WARPS) * 32;
 
@@ -192,15 +197,16 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
     }
   } else if (warp < DX_W_TMA) {
     // ================================ operand remainders ================================
-    const int g = warp;
-    const int tt = lane;
+    const int g = warp / (DX_GROUP / 32);
+    const int tt = tid - g * DX_GROUP;
     constexpr int A_CH = SLABS * SLAB_BYTES / 16, B_CH = B_BYTES / 16;
     static_assert(A_CH % DX_GROUP == 0 && B_CH % DX_GROUP == 0, "chunks must divide over the group");
-    uint8_t* st = smem + g * STAGE_BYTES;
     const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)nkc;
-    for (uint32_t it = g; it < n_it; it += STAGES) {
+    for (uint32_t it = g; it < n_it; it += DX_NGROUPS) {
+      const int sidx = (int)(it % STAGES);
+      uint8_t* st = smem + sidx * STAGE_BYTES;
       const uint32_t ph = (it / STAGES) & 1;
-      tc::bounded_wait(&raw_full[g], ph);
+      tc::bounded_wait(&raw_full[sidx], ph);
 #pragma unroll
       for (int q0 = 0; q0 < A_CH / DX_GROUP; q0 += 4) {
         float4 x[4];
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
                           x[q].w - trunc_tf32(x[q].w));
       }
       tc::fence_proxy_async();
-      mbar_arrive(&ops_ready[g]);
+      mbar_arrive(&ops_ready[sidx]);
     }
   } else {
     // ================================ epilogue (16 warps) ================================
