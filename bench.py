@@ -330,8 +330,8 @@ def main():
         batch.data.record_stream(cur)
         for v in batch.domain.values():
             v.record_stream(cur)
-        pending['next'] = prefetch(i + 1)
         loss = model.training_step(batch, i)
+        pending['next'] = prefetch(i + 1)         # issued once this step's graph is enqueued: off the launch critical path
         for p in params:
             p.grad = None
         loss.backward()
