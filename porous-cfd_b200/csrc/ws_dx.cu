@@ -465,8 +465,12 @@ extern "C" int pcfd_ws_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, i
   ws::DxArgs a{zin, zin_ps, ldzin, gzin, gzin_ps, ldgzin, gescale, ldgescale, rows, rows_per_geom, k, n,
                make_intrans(tin, k), 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
+  // few row tiles (per-geometry layers): 64-column passes double the number of CTAs; otherwise 128-column tiles
+  const int pts = 32 * (8 / cj);
+  const int64_t items128 = ((rows + pts - 1) / pts) * ((k + 127) / 128);
+  const bool narrow = k <= 64 || items128 * 2 <= ws::num_sms();
 #define PCFD_WS_DX(CJ_)                                                             \
-  return k <= 64 ? ws::launch_dx<CJ_, 64>(gzout, gzout_ps, ldgzout, w, ldw, a, st)  \
+  return narrow ? ws::launch_dx<CJ_, 64>(gzout, gzout_ps, ldgzout, w, ldw, a, st)  \
                  : ws::launch_dx<CJ_, 128>(gzout, gzout_ps, ldgzout, w, ldw, a, st);
   switch (cj) {
     case 1: PCFD_WS_DX(1)

@@ -376,8 +376,12 @@ extern "C" int pcfd_ws_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t 
   ws::FwdArgs a{nullptr, 0, 0, bias, cvec, ldcvec, rows, rows_per_geom, k, n, make_intrans(tin, k), 0, 0, 0, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (cj == 1) { zin_ps = (int64_t)rows * ldzin; zout_ps = (int64_t)rows * ldzout; }
+  // few row tiles (per-geometry layers): 64-column passes double the number of CTAs; otherwise 128-column tiles
+  const int pts = 32 * (8 / cj);
+  const int64_t items128 = ((rows + pts - 1) / pts) * ((n + 127) / 128);
+  const bool narrow = n <= 64 || items128 * 2 <= ws::num_sms();
 #define PCFD_WS_FWD(CJ_)                                                                                          \
-  return n <= 64 ? ws::launch_fwd<CJ_, 64>(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, a, st)              \
+  return narrow ? ws::launch_fwd<CJ_, 64>(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, a, st)              \
                  : ws::launch_fwd<CJ_, 128>(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, a, st);
   switch (cj) {
     case 1: PCFD_WS_FWD(1)
