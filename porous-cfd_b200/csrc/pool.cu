@@ -70,21 +70,44 @@ __global__ void __launch_bounds__(256) segmax_short_fwd_kernel(const float* __re
   const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   const int col = blockIdx.y * 128 + lane * 4;
-  if (col >= c) return;
+  const bool active = col < c;            // no early exit: the whole warp takes part in the ballots below
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
   int bi[4] = {-1, -1, -1, -1};
   const float* base = z + seg * (int64_t)seg_len * ldz + col;
-  for (int j = 0; j < seg_len; ++j) {
-    if (slots != nullptr && __ldg(slots + seg * seg_len + j) < 0) continue;
-    const float4 x = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * ldz));
-    const float v[4] = {act_value(act, x.x), act_value(act, x.y), act_value(act, x.z), act_value(act, x.w)};
+  // slot validity of up to 96 slots as three ballot words (lane j looks at slots j, j+32, j+64), so that the row loop
+  // below has no dependent loads in front of its data loads and can keep several rows in flight
+  unsigned valid[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};
+  if (slots != nullptr) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (v[e] > best[e] || bi[e] < 0) { best[e] = v[e]; bi[e] = j; }
+    for (int w = 0; w < 3; ++w) {
+      const int j = w * 32 + lane;
+      const bool ok = j < seg_len && __ldg(slots + seg * seg_len + j) >= 0;
+      valid[w] = __ballot_sync(0xffffffffu, ok);
+    }
+  }
+  for (int j0 = 0; j0 < seg_len; j0 += 4) {
+    float4 x[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const unsigned word = j < 32 ? valid[0] : (j < 64 ? valid[1] : valid[2]);
+      ok[u] = active && j < seg_len && ((word >> (j & 31)) & 1u);
+      if (ok[u]) x[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)j * ldz));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int j = j0 + u;
+      const float v[4] = {act_value(act, x[u].x), act_value(act, x[u].y), act_value(act, x[u].z), act_value(act, x[u].w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (v[e] > best[e] || bi[e] < 0) { best[e] = v[e]; bi[e] = j; }
+    }
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    if (col + e < c) {
+    if (active && col + e < c) {
       out[seg * ldout + col + e] = bi[e] >= 0 ? best[e] : 0.0f;
       arg[seg * c + col + e] = bi[e];
     }
