@@ -13,7 +13,8 @@
 // CTA.  grid = (passes over the (n, k) plane, row splits); the splits' partial products are reduced in a
 // fixed order by pcfd_dw_finish (deterministic), which also forms the bias / per-geometry gradients.
 //
-//   warps 0-15  four groups of 4 warps; group g transforms ring iterations g, g+4, ...: activation jet /
+//   warps 0-15  1-4 transform groups (plan_dw: few large groups for short rings); group g transforms ring iterations
+//               g, g + groups, ...: activation jet /
 //               dropout / branch scaling of the zin tile in place (= TF32 "hi" operand, the tensor core
 //               reads the top 19 bits) and the exact remainders lo = x - trunc_tf32(x) of both operands;
 //               after the main loop the same warps drain the accumulators to the partial buffer

@@ -9,8 +9,8 @@
 //
 //   warp 16     TMA producer: raw fp32 tiles of the pre-activation jets (3-D map, 64B swizzle) and of
 //               the weights into a 4-stage ring (16 contraction entries per stage)
-//   warps 0-15  transform, four groups of 4 warps, group g owns ring stage g (so the four stages are
-//               transformed concurrently): activation jet / dropout / branch scaling in shared memory,
+//   warps 0-15  transform, NGROUPS groups (2 groups of 8 warps: measured best of 4x4 / 2x8 / 1x16), group g takes ring
+//               iterations g, g + NGROUPS, ...: activation jet / dropout / branch scaling in shared memory,
 //               in place (the tensor core reads the top 19 bits of an fp32 word, so the transformed fp32
 //               tile IS the TF32 "hi" operand) + the exact remainder lo = x - trunc_tf32(x) into a
 //               second tile
