@@ -53,7 +53,7 @@ int pcfd_ws_jet_linear_bwd_dw_partials(const float*, int64_t, int32_t, const flo
 int pcfd_ws_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*,
                            const float*, int32_t, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t,
                            int32_t, void*);
-int pcfd_ws_fwd1_enabled(void);
+int pcfd_ws_fwd1_enabled(int32_t);
 int pcfd_ws_jet_linear_fwd1(const float*, int32_t, const pcfd_intrans_t*, const float*, int32_t, const float*, const float*,
                             int32_t, float*, int32_t, int64_t, int64_t, int32_t, int32_t, void*);
 #endif
@@ -104,7 +104,7 @@ extern "C" int pcfd_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_t ldz
   if (rc) return rc;
 #ifdef PCFD_HAVE_TC
   if (g_engine == 2 && pcfd_ws_supported_fwd(zin, zin_ps, ldzin, w, ldw, zout, zout_ps, ldzout, cj, rows, k, n)) {
-    if (cj == 1 && pcfd_ws_fwd1_enabled())   // value-only layer: A operand through tensor memory
+    if (cj == 1 && pcfd_ws_fwd1_enabled(k))   // value-only layer: A operand through tensor memory
       return pcfd_ws_jet_linear_fwd1(zin, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, ldzout, rows, rows_per_geom, k, n,
                                      stream);
     return pcfd_ws_jet_linear_fwd(zin, zin_ps, ldzin, tin, w, ldw, bias, cvec, ldcvec, zout, zout_ps, ldzout, cj, rows,

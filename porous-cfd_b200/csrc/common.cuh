@@ -130,9 +130,11 @@ __host__ __device__ __forceinline__ uint32_t dropout_row_hash(uint32_t hseed, in
 }
 __device__ __forceinline__ float dropout_from_row(uint32_t hrow, int64_t row, int col, float p, float inv_keep) {
   const uint32_t h = mix32(hrow + 0x9e3779b9U * (uint32_t)col + (uint32_t)((uint64_t)row >> 32));
-  // uniform in [0,1): keep when u >= p
-  const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+  // u = (h >> 8) / 2^24 is uniform in [0,1): keep when u >= p.  Both sides scaled by 2^24 are exact, so the test is the
+  // integer comparison (h >> 8) >= ceil(p * 2^24); the threshold is loop-invariant and the int->float conversion (an
+  // XU-pipe instruction, like the activation's MUFU ops) goes away
+  const uint32_t thr = (uint32_t)ceilf(p * 16777216.0f);
+  return (h >> 8) >= thr ? inv_keep : 0.0f;
 }
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t salt, int64_t row, int col, float p, float inv_keep) {
   return dropout_from_row(dropout_row_hash(dropout_seed_hash(seed, salt), row), row, col, p, inv_keep);

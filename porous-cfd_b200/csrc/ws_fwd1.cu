@@ -52,6 +52,31 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
+// transform of one point's 16 staged entries (columns col0 .. col0+15, all inside the transformed range): straight-line,
+// so that the 16 independent activation / dropout chains interleave
+template <int ACT, bool DROP>
+__device__ __forceinline__ void f1_row(const uint8_t* st, int point, const InTrans& tin, uint32_t hseed, int64_t row,
+                                       int64_t geom, int col0, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+  float x[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(st + swz<64>(point, j));
+    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+  }
+  const uint32_t hrow = DROP ? dropout_row_hash(hseed, row) : 0u;
+  const float* es = tin.escale != nullptr ? tin.escale + geom * tin.ldescale + col0 : nullptr;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float sc = 1.0f;
+    if (DROP) sc = dropout_from_row(hrow, row, col0 + e, tin.drop_p, tin.inv_keep);
+    if (es != nullptr) sc *= __ldg(es + e);
+    float zz[1] = {x[e]};
+    jet_act_fwd_t<1, ACT>(sc, zz);
+    hi[e] = __float_as_uint(zz[0]);
+    lo[e] = __float_as_uint(zz[0] - trunc_tf32(zz[0]));
+  }
+}
+
 struct Fwd1Args {
   const float* bias; const float* cvec; int ldcvec;
   int64_t rows, rows_per_geom; int k, n;
@@ -159,6 +184,7 @@ __global__ void __launch_bounds__(F1_THREADS, 1) ws_fwd1_kernel(const __grid_con
     const uint32_t hseed = dropout_seed_hash(seed, a.tin.salt);
     const bool scaled = a.tin.escale != nullptr || a.tin.drop_p > 0.0f;
     const bool plain = a.tin.act == PCFD_ACT_NONE && !scaled;
+    const bool drop = a.tin.drop_p > 0.0f;
     const uint32_t n_it = (uint32_t)my_tiles * (uint32_t)nkc;
     for (uint32_t it = g; it < n_it; it += F1_GROUPS) {
       const int s = (int)(it % F1_STAGES);
@@ -166,7 +192,9 @@ __global__ void __launch_bounds__(F1_THREADS, 1) ws_fwd1_kernel(const __grid_con
       const uint32_t tl = it / (uint32_t)nkc;
       const int kc = (int)(it - tl * (uint32_t)nkc);
       const int t = (int)blockIdx.x + (int)tl * (int)gridDim.x;
-      const int64_t row = (int64_t)(t / a.n_passes) * 128 + point;
+      int64_t row = (int64_t)(t / a.n_passes) * 128 + point;
+      if (row >= a.rows) row = a.rows - 1;   // rows past the end are zero-filled by TMA and clipped by the store
+      const int64_t geom = a.tin.escale != nullptr ? geom_of(row, a.rows_per_geom) : 0;
       uint8_t* st = smem + s * STAGE_BYTES;
       uint8_t* bt = st + F1_A_BYTES;
       tc::bounded_wait(&raw_full[s], ph);
@@ -181,19 +209,32 @@ __global__ void __launch_bounds__(F1_THREADS, 1) ws_fwd1_kernel(const __grid_con
       }
       // ---- A: this point's 16 entries -> registers -> transform -> TMEM (hi, lo)
       uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(st + swz<64>(point, j));
-        float v[1][4] = {{x.x, x.y, x.z, x.w}};
-        const int col0 = kc * BK + j * 4;
-        if (!plain && row < a.rows && col0 < a.tin.act_cols) {
-          const int64_t geom = a.tin.escale != nullptr ? geom_of(row, a.rows_per_geom) : 0;
-          transform_dispatch<1>(v, a.tin, scaled, hseed, row, geom, col0, a.tin.act_cols - col0);
+      const int col0 = kc * BK;
+      if (plain || col0 + BK <= a.tin.act_cols) {
+        // whole chunk inside the transformed columns: one straight-line body for the 16 independent entries
+        if (plain) f1_row<PCFD_ACT_NONE, false>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+        else if (a.tin.act == PCFD_ACT_SILU) {
+          if (drop) f1_row<PCFD_ACT_SILU, true>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+          else f1_row<PCFD_ACT_SILU, false>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+        } else if (a.tin.act == PCFD_ACT_TANH) {
+          if (drop) f1_row<PCFD_ACT_TANH, true>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+          else f1_row<PCFD_ACT_TANH, false>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+        } else {
+          if (drop) f1_row<PCFD_ACT_NONE, true>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
+          else f1_row<PCFD_ACT_NONE, false>(st, point, a.tin, hseed, row, geom, col0, hi, lo);
         }
+      } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[4 * j + e] = __float_as_uint(v[0][e]);
-          lo[4 * j + e] = __float_as_uint(v[0][e] - trunc_tf32(v[0][e]));
+        for (int j = 0; j < 4; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(st + swz<64>(point, j));
+          float v[1][4] = {{x.x, x.y, x.z, x.w}};
+          const int c0 = col0 + j * 4;
+          if (c0 < a.tin.act_cols) transform_dispatch<1>(v, a.tin, scaled, hseed, row, geom, c0, a.tin.act_cols - c0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[4 * j + e] = __float_as_uint(v[0][e]);
+            lo[4 * j + e] = __float_as_uint(v[0][e] - trunc_tf32(v[0][e]));
+          }
         }
       }
       const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + F1_A_TMEM + (uint32_t)s * 32;
@@ -328,10 +369,17 @@ using namespace pcfd;
 
 // value-only forward with the A operand in tensor memory (same preconditions as pcfd_ws_supported_fwd, cj = 1);
 // PCFD_FWD1=0 keeps such layers on the general kernel
-extern "C" int pcfd_ws_fwd1_enabled(void) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("PCFD_FWD1"); on = e ? atoi(e) : 1; }
-  return on;
+// ... and layers with fewer than PCFD_FWD1_MIN_K (default 32) input columns, whose single ring stage leaves the
+// time in the epilogue, where the general kernel has twice the warps
+extern "C" int pcfd_ws_fwd1_enabled(int32_t k) {
+  static int on = -1, min_k = 32;
+  if (on < 0) {
+    const char* m = getenv("PCFD_FWD1_MIN_K");
+    if (m) min_k = atoi(m);
+    const char* e = getenv("PCFD_FWD1");
+    on = e ? atoi(e) : 1;
+  }
+  return on && k >= min_k;
 }
 
 extern "C" int pcfd_ws_jet_linear_fwd1(const float* zin, int32_t ldzin, const pcfd_intrans_t* tin, const float* w,
