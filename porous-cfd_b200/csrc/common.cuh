@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include "../../include/pcfd.h"
 
 #define PCFD_CHECK_LAUNCH()                                   \
@@ -12,6 +15,36 @@
   } while (0)
 
 namespace pcfd {
+
+// PCFD_PDL=0 launches everything fully serialised
+inline int pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PCFD_PDL"); on = e ? atoi(e) : 1; }
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// A kernel launched through launch_pdl may become resident while its predecessor in the stream is still running: its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail, and griddep_wait()
+// holds it until the predecessor has completed and its writes are visible.  Nothing before griddep_wait() may touch
+// global memory.  griddep_launch_dependents() lets the NEXT kernel of the stream be scheduled as SMs free up.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 
 // ---- jet layout: cj -> (spatial dims D, derivative order) ---------------------------------
 template <int CJ> struct JetShape;

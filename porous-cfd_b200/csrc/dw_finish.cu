@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(256) dw_finish_kernel(const float* __restrict_
                                                         float* gbias, float* gcvec, int ldgcvec) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  griddep_wait();            // launched through launch_pdl right behind the dW kernel that writes `partial`
   if ((int)blockIdx.x < gw_blocks) {
     // ---- weight gradient: element = blockIdx.x * 32 + lane, split lane wy
     const int64_t total = (int64_t)n * k;
@@ -203,9 +204,9 @@ extern "C" int pcfd_dw_finish(const float* partial, int splits, const float* gzo
   if (do_gw || do_cs) {
     const int gw_blocks = do_gw ? (int)(((int64_t)n * k + 31) / 32) : 0;
     const int cs_blocks = do_cs ? (n + 31) / 32 : 0;
-    dw_finish_kernel<<<(unsigned)(gw_blocks + cs_blocks), 256, 0, st>>>(partial, splits, n, k, gw, ldgw, gw_blocks, sums,
-                                                                        chunks, subs, gbias, gcvec, ldgcvec);
-    PCFD_CHECK_LAUNCH();
+    const cudaError_t le = launch_pdl(dw_finish_kernel, dim3((unsigned)(gw_blocks + cs_blocks)), dim3(256), (size_t)0, st,
+                                      partial, splits, n, k, gw, ldgw, gw_blocks, sums, chunks, subs, gbias, gcvec, ldgcvec);
+    if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   }
   return PCFD_OK;
 }

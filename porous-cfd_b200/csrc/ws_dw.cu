@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  griddep_wait();                  // everything above overlaps the tail of the previous kernel of the stream
+  griddep_launch_dependents();     // one resident wave: the next kernel may take SMs as they free up
 
   if (warp == DW_W_TMA) {
     // ================================ TMA producer ================================
@@ -311,8 +313,17 @@ __global__ void __launch_bounds__(DW_THREADS, 1) ws_dw_kernel(const __grid_const
   if (warp == DW_W_MMA) tc::tmem_dealloc(tmem_base, 512);
 }
 
+}  // namespace ws
+}  // namespace pcfd
+
+#include "ws_dw1.cuh"
+
+namespace pcfd {
+namespace ws {
+
 // ---- host: pass / split plan -------------------------------------------------------------------
 struct DwPlan {
+  int kind;                           // 0: ws_dw_kernel (operands in shared memory), 1: ws_dw1_kernel (cj = 1, gzout in TMEM)
   int r, e, nt, mt, ntl, passes_n, passes_k, stages, groups, splits;
   int64_t rows_per_split;
   int64_t chunks, rows_per_chunk;     // column-sum scratch of pcfd_dw_finish
@@ -336,8 +347,86 @@ static inline void dw_ring(int fit, int* stages, int* groups) {
   while (*groups > PCFD_DW_MAX_GROUPS || (*groups > 0 && *stages % *groups != 0)) --*groups;
 }
 
+// row splits of a pass plan: one CTA per (pass, split), at least a few ring iterations each
+static void plan_splits(DwPlan& p, int cj, int64_t rows, int64_t rows_per_geom) {
+  p.e = cj * p.r;
+  const int passes = p.passes_n * p.passes_k;
+  int64_t splits = num_sms() / passes;
+  if (splits < 1) splits = 1;
+  // at least a few ring iterations per CTA.  Measured (PCFD_DW_MIN_ITERS = 2..64 on the abc layers): a CTA's pipeline is
+  // latency-bound, so more, shorter splits win over fewer partials -- 8 and below are equal, 32 costs 20-50 % on the
+  // small layers
+  static int min_iters = -1;
+  if (min_iters < 0) { const char* e = getenv("PCFD_DW_MIN_ITERS"); min_iters = e ? atoi(e) : 8; }
+  const int64_t min_rows = (int64_t)min_iters * p.r;
+  const int64_t max_splits = (rows + min_rows - 1) / min_rows;
+  if (splits > max_splits) splits = max_splits;
+  int64_t rps = (rows + splits - 1) / splits;
+  rps = (rps + p.r - 1) / p.r * p.r;
+  p.rows_per_split = rps;
+  p.splits = (int)((rows + rps - 1) / rps);
+  p.rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
+  p.chunks = (rows + p.rows_per_chunk - 1) / p.rows_per_chunk;
+}
+
+
+// ring of the TMEM-operand kernel: groups are 4 warps (one per TMEM lane quarter) and divide the ring depth
+static inline void dw1_ring(int fit, int* stages, int* groups) {
+  if (fit >= 8) { *stages = 8; *groups = 4; }
+  else if (fit >= 6) { *stages = 6; *groups = 3; }
+  else if (fit >= 4) { *stages = 4; *groups = 4; }
+  else if (fit >= 2) { *stages = fit; *groups = fit; }
+  else { *stages = 0; *groups = 0; }
+}
+
+// PCFD_DW1=0 keeps value-only layers on ws_dw_kernel; PCFD_DW1_R = 16 / 32 forces the rows per stage
+static int dw1_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("PCFD_DW1"); on = e ? atoi(e) : 1; }
+  return on;
+}
+
+static DwPlan plan_dw1(int64_t rows, int64_t rows_per_geom, int k, int n) {
+  DwPlan p{};
+  p.kind = 1;
+  p.nt = k <= 64 ? 64 : 128;
+  const int mt_all = (n + 127) / 128, ntl_all = (k + p.nt - 1) / p.nt;
+  static int force_r = -1;
+  if (force_r < 0) { const char* e = getenv("PCFD_DW1_R"); force_r = e ? atoi(e) : 0; }
+  double best = 1e300;
+  for (int r = 16; r <= 32; r *= 2) {
+    if (force_r && r != force_r) continue;
+    for (int mt = 1; mt <= mt_all && mt <= 4; ++mt) {
+      for (int ntl = 1; ntl <= ntl_all; ++ntl) {
+        const int acc = mt * ntl * p.nt;                       // accumulator columns; the rest of TMEM holds operand slots
+        if (acc + 2 * mt * 2 * r > 512) continue;
+        const int stage_bytes = (mt * 4 + 2 * ntl * p.nt / 32) * (r * 128);
+        int fit = DW_SMEM_MAX / stage_bytes;
+        if ((512 - acc) / (mt * 2 * r) < fit) fit = (512 - acc) / (mt * 2 * r);
+        int stages = 0, groups = 0;
+        dw1_ring(fit, &stages, &groups);
+        if (stages < 2) continue;
+        const int pn = (mt_all + mt - 1) / mt, pk = (ntl_all + ntl - 1) / ntl;
+        double cost = (double)n * pk + (double)k * pn;
+        if (stages < 3) cost *= 1.5;
+        if (r == 32 && stages >= 4) cost *= 0.999;             // same traffic: prefer the longer stage
+        if (cost < best - 1e-9) {
+          best = cost; p.mt = mt; p.ntl = ntl; p.stages = stages; p.groups = groups; p.passes_n = pn; p.passes_k = pk; p.r = r;
+        }
+      }
+    }
+  }
+  if (p.stages >= 2) plan_splits(p, 1, rows, rows_per_geom);
+  return p;
+}
+
 static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n) {
+  if (cj == 1 && dw1_enabled()) {
+    const DwPlan p1 = plan_dw1(rows, rows_per_geom, k, n);
+    if (p1.stages >= 2) return p1;
+  }
   DwPlan p;
+  p.kind = 0;
   p.nt = k <= 64 ? 64 : 128;
   const int mt_all = (n + 127) / 128, ntl_all = (k + p.nt - 1) / p.nt;
   static int force_r = -1;
@@ -367,24 +456,7 @@ static DwPlan plan_dw(int cj, int64_t rows, int64_t rows_per_geom, int k, int n)
       }
     }
   }
-  p.e = cj * p.r;
-  const int passes = p.passes_n * p.passes_k;
-  int64_t splits = num_sms() / passes;
-  if (splits < 1) splits = 1;
-  // at least a few ring iterations per CTA.  Measured (PCFD_DW_MIN_ITERS = 2..64 on the abc layers): a CTA's pipeline is
-  // latency-bound, so more, shorter splits win over fewer partials -- 8 and below are equal, 32 costs 20-50 % on the
-  // small layers
-  static int min_iters = -1;
-  if (min_iters < 0) { const char* e = getenv("PCFD_DW_MIN_ITERS"); min_iters = e ? atoi(e) : 8; }
-  const int64_t min_rows = (int64_t)min_iters * p.r;
-  const int64_t max_splits = (rows + min_rows - 1) / min_rows;
-  if (splits > max_splits) splits = max_splits;
-  int64_t rps = (rows + splits - 1) / splits;
-  rps = (rps + p.r - 1) / p.r * p.r;
-  p.rows_per_split = rps;
-  p.splits = (int)((rows + rps - 1) / rps);
-  p.rows_per_chunk = rows_per_geom > 0 ? rows_per_geom : 2048;
-  p.chunks = (rows + p.rows_per_chunk - 1) / p.rows_per_chunk;
+  plan_splits(p, cj, rows, rows_per_geom);
   return p;
 }
 
@@ -414,8 +486,41 @@ static int launch_dw(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
     configured = DW_SMEM_MAX + 1024;
   }
   dim3 grid((unsigned)(p.passes_n * p.passes_k), (unsigned)p.splits);
-  ws_dw_kernel<CJ, R, NT><<<grid, DW_THREADS, smem, st>>>(tmG, tmZ, a);
-  PCFD_CHECK_LAUNCH();
+  const cudaError_t le = launch_pdl(ws_dw_kernel<CJ, R, NT>, grid, dim3(DW_THREADS), (size_t)smem, st, tmG, tmZ, a);
+  if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
+  return PCFD_OK;
+}
+
+
+template <int R, int NT>
+static int launch_dw1(const float* gzout, int ldgzout, const float* zin, int ldzin, DwArgs a, const DwPlan& p, cudaStream_t st) {
+  CUtensorMap tmG, tmZ;
+  {
+    const uint64_t dims[2] = {(uint64_t)a.n, (uint64_t)a.rows};
+    const uint64_t str[1] = {(uint64_t)ldgzout * 4};
+    const uint32_t box[2] = {32, (uint32_t)R};
+    if (!make_tmap(&tmG, gzout, 2, dims, str, box, SW128_ATOM32)) return PCFD_ERR_ARG;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a.k, (uint64_t)a.rows};
+    const uint64_t str[1] = {(uint64_t)ldzin * 4};
+    const uint32_t box[2] = {32, (uint32_t)R};
+    if (!make_tmap(&tmZ, zin, 2, dims, str, box, SW128_ATOM32)) return PCFD_ERR_ARG;
+  }
+  const int stage_bytes = (p.mt * 4 + 2 * p.ntl * NT / 32) * (R * 128);
+  int smem = p.stages * stage_bytes;
+  if (smem < 4 * 4 * 128 * 4) smem = 4 * 4 * 128 * 4;          // the column sums of the groups reuse the ring
+  smem += 1024;
+  if (smem > DW_SMEM_MAX + 1024) return PCFD_ERR_ARG;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ws_dw1_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_MAX + 1024);
+    if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+    configured = true;
+  }
+  dim3 grid((unsigned)(p.passes_n * p.passes_k), (unsigned)p.splits);
+  const cudaError_t le = launch_pdl(ws_dw1_kernel<R, NT>, grid, dim3(DW1_THREADS), (size_t)smem, st, tmG, tmZ, a);
+  if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;
 }
 
@@ -456,6 +561,13 @@ extern "C" int pcfd_ws_jet_linear_bwd_dw_partials(const float* gzout, int64_t gz
                want_colsum ? reinterpret_cast<float*>(workspace) + (size_t)p.splits * n * k : nullptr};
   *splits_out = p.splits;
   cudaStream_t st = (cudaStream_t)stream;
+  if (p.kind == 1) {
+    if (p.r == 16)
+      return p.nt == 64 ? ws::launch_dw1<16, 64>(gzout, ldgzout, zin, ldzin, a, p, st)
+                        : ws::launch_dw1<16, 128>(gzout, ldgzout, zin, ldzin, a, p, st);
+    return p.nt == 64 ? ws::launch_dw1<32, 64>(gzout, ldgzout, zin, ldzin, a, p, st)
+                      : ws::launch_dw1<32, 128>(gzout, ldgzout, zin, ldzin, a, p, st);
+  }
 #define PCFD_WS_DW(CJ_, R_)                                                                                    \
   if (p.r == R_)                                                                                               \
     return p.nt == 64 ? ws::launch_dw<CJ_, R_, 64>(gzout, gzout_ps, ldgzout, zin, zin_ps, ldzin, a, p, st)     \

@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(DX_THREADS, 1) ws_dx_kernel(const __grid_const
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  griddep_wait();                  // everything above overlaps the tail of the previous kernel of the stream
+  griddep_launch_dependents();     // one resident wave: the next kernel may take SMs as they free up
 
   const int total_tiles = a.row_tiles * a.k_passes;
   const int nkc = (a.n + BK - 1) / BK;                  // contraction chunks (over the layer's outputs)
@@ -433,8 +435,8 @@ static int launch_dx(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
   }
   const int total = a.row_tiles * a.k_passes;
   const int grid = total < num_sms() ? total : num_sms();
-  ws_dx_kernel<CJ, NT><<<grid, DX_THREADS, SMEM, st>>>(tmG, tmW, tmO, a);
-  PCFD_CHECK_LAUNCH();
+  const cudaError_t le = launch_pdl(ws_dx_kernel<CJ, NT>, dim3(grid), dim3(DX_THREADS), (size_t)SMEM, st, tmG, tmW, tmO, a);
+  if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;
 }
 

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(THREADS, 1) ws_fwd_kernel(const __grid_constan
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  griddep_wait();                  // everything above overlaps the tail of the previous kernel of the stream
+  griddep_launch_dependents();     // one resident wave: the next kernel may take SMs as they free up
 
   const int total_tiles = a.row_tiles * a.n_passes;
   const int nkc = (a.k + BK - 1) / BK;
@@ -346,8 +348,8 @@ static int launch_fwd(const float* zin, int64_t zin_ps, int ldzin, const float* 
   }
   const int total = a.row_tiles * a.n_passes;
   const int grid = total < num_sms() ? total : num_sms();
-  ws_fwd_kernel<CJ, NT><<<grid, THREADS, SMEM, st>>>(tmZ, tmW, tmO, a);
-  PCFD_CHECK_LAUNCH();
+  const cudaError_t le = launch_pdl(ws_fwd_kernel<CJ, NT>, dim3(grid), dim3(THREADS), (size_t)SMEM, st, tmZ, tmW, tmO, a);
+  if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;
 }
 

@@ -34,24 +34,6 @@ constexpr int F1_A_BYTES = 128 * 64;                 // raw A tile of a stage
 constexpr uint32_t F1_A_TMEM = 256;                  // first operand column (accumulators use [0, 2*NT))
 static_assert(F1_STAGES % F1_GROUPS == 0, "a group must see every use of its stages");
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-
 // transform of one point's 16 staged entries (columns col0 .. col0+15, all inside the transformed range): straight-line,
 // so that the 16 independent activation / dropout chains interleave
 template <int ACT, bool DROP>
@@ -118,6 +100,8 @@ __global__ void __launch_bounds__(F1_THREADS, 1) ws_fwd1_kernel(const __grid_con
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  griddep_wait();                  // everything above overlaps the tail of the previous kernel of the stream
+  griddep_launch_dependents();     // one resident wave: the next kernel may take SMs as they free up
 
   const int total_tiles = a.row_tiles * a.n_passes;
   const int nkc = (a.k + BK - 1) / BK;
@@ -357,8 +341,8 @@ static int launch_fwd1(const float* zin, int ldzin, const float* w, int ldw, flo
   }
   const int total = a.row_tiles * a.n_passes;
   const int grid = total < num_sms() ? total : num_sms();
-  ws_fwd1_kernel<NT><<<grid, F1_THREADS, SMEM, st>>>(tmZ, tmW, tmO, a);
-  PCFD_CHECK_LAUNCH();
+  const cudaError_t le = launch_pdl(ws_fwd1_kernel<NT>, dim3(grid), dim3(F1_THREADS), (size_t)SMEM, st, tmZ, tmW, tmO, a);
+  if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;
 }
 
