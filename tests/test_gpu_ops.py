@@ -222,6 +222,11 @@ CASES = [  # cj, dims, order, rows, rows_per_geom, k, n, act, use_escale, use_cv
     (4, 3, 1, 4096, 2048, 3, 64, None, False, False),     # first layer, k = D
     (1, 0, 0, 6000, 0, 7, 64, None, False, False),        # first layer of a value-only encoder
     (5, 2, 2, 3000, 1500, 128, 8, 'tanh', False, True),
+    # value-only layers on the tensor-memory-operand kernels (ws_fwd1.cu, ws_dw1.cuh): two output tiles with a ragged
+    # second one, branch scaling + per-geometry constant, a contraction that ends inside a ring stage
+    (1, 0, 0, 2048, 512, 96, 160, 'silu', True, True),
+    (1, 0, 0, 3000, 0, 384, 128, 'tanh', False, False),
+    (1, 0, 0, 1500, 0, 40, 300, 'silu', False, False),
 ]
 
 
@@ -283,10 +288,24 @@ def test_jet_linear_forward_backward(ops, case):
     assert rel_l2(gw.cpu().double(), 2 * wr.grad) < GEMM_TOL
 
 
-def test_dropout_mask_is_consistent_between_passes(ops):
+def test_jet_linear_with_fallback_kernels():
+    """The same layer cases with the tensor-memory-operand kernels and programmatic dependent launch switched off
+    (PCFD_FWD1=0 PCFD_DW1=0 PCFD_PDL=0): the general engine-2 kernels stay correct for value-only layers."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PCFD_FWD1='0', PCFD_DW1='0', PCFD_PDL='0')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-m', 'gpu', '-k',
+                        'test_jet_linear_forward_backward or test_dropout_mask'], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize('cj', [4, 1])
+def test_dropout_mask_is_consistent_between_passes(ops, cj):
     """The same (seed, salt) must give the same mask in forward, dX and dW; keep-rate ~ 1-p."""
     from porous_cfd_b200.ops import Jet
-    cj, rows, k, n, p = 4, 512, 64, 32, 0.25
+    rows, k, n, p = 512, 64, 32, 0.25
     g = torch.Generator().manual_seed(0)
     zj = Jet.empty(cj, rows, k, 'cuda'); zj.t.copy_(torch.randn(cj, rows, k, generator=g))
     w = torch.eye(k, device='cuda')[:n].contiguous()                 # zout = first n transformed inputs
@@ -302,6 +321,12 @@ def test_dropout_mask_is_consistent_between_passes(ops):
     gj = Jet(torch.ones(cj, rows, n, device='cuda'), n)
     gz = ops.jet_linear_bwd_dx(gj, w, 0, zj, tin, None, 0, k, n).t[:, :, :n]
     assert torch.equal(gz[0] != 0, kept)
+    # dW with gzout = 1: every row of gw is the column sum of the transformed input, i.e. of `out` where w is the identity
+    gw = torch.zeros(n, k, device='cuda')
+    ws = torch.empty(ops.dw_workspace_bytes(cj, rows, 0, k, n), dtype=torch.uint8, device='cuda')
+    ops.jet_linear_bwd_dw(gj, zj, tin, gw, 0, None, None, 0, k, n, ws)
+    want = out.double().sum(dim=(0, 1))
+    assert rel_l2(gw[0, :n].cpu().double(), want.cpu()) < 1e-5
     # another step seed gives another mask
     ops.advance_seed(seed)
     out2 = ops.jet_linear_fwd(zj, tin, w, 0, k, None, None, 0, n).t[0, :, :n]
