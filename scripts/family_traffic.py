@@ -27,7 +27,12 @@ def main(src, dst):
     for d in per.values():
         n = d['name']
         m = re.search(r'(ws_fwd|ws_dx|ws_dw|jet_fwd|jet_dx|jet_dw|thin_n_fwd|thin_k_fwd|thin_n_dx|small_rows_dw|small_rows)_?kernel<(\d+)', n)
-        if m:
+        m1 = re.search(r'(ws_fwd1|ws_dw1)_kernel<', n)      # value-only kernels with the operand in tensor memory
+        if m1:
+            last = 'jet_fwd_cj1' if m1.group(1) == 'ws_fwd1' else 'jet_dw_cj1'
+            fam[last]['calls'] += 1
+            fam[last]['bytes'] += d['bytes']
+        elif m:
             kind, cj = m.group(1), int(m.group(2))
             if kind == 'small_rows':
                 cj, p = 1, ('dx' if '<1>' in n or '<true>' in n else 'fwd')

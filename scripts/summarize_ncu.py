@@ -26,6 +26,8 @@ def launches(src, dst, title):
     lines = [l for l in open(src) if not l.startswith('==')]
     tot = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
+        if row.get('Metric Name', 'gpu__time_duration.sum') != 'gpu__time_duration.sum':
+            continue     # captures that also carry dram__bytes_* (scripts/family_traffic.py reads those)
         try:
             v = float(row['Metric Value'].replace(',', ''))
         except (ValueError, KeyError):
