@@ -272,6 +272,32 @@ int pcfd_zero(float* p, int64_t n, void* stream);
 /* *seed_dev = mix(*seed_dev) : advances the dropout seed once per step without a host round trip */
 int pcfd_advance_seed(uint64_t* seed_dev, void* stream);
 
+/*
+ * Batch ingestion on the device.  `data` is the dataset tensor [n_geom][n_points][f] with the
+ * internal points of every geometry in rows [0, n_internal) and its boundary points behind them (the row order
+ * FoamDataset.load_case produces, dataset/foam_dataset.py:424-433).
+ *
+ * pcfd_sdf_feature: FoamDataset.add_sdf (dataset/foam_dataset.py:360-380).  data[g][p][sdf_col] = distance of point p
+ * to the nearest boundary point of geometry g (scipy cdist + min), divided by the largest such distance of the
+ * geometry, times (0.5 - data[g][p][region_col]) * 2 for the internal points (region_col < 0: no sign).  Coordinates
+ * are columns pos_col .. pos_col+dims-1, multiplied by coord_scale[dims] first (device pointer or NULL: the `range` /
+ * `std` of the coordinate scaler, whose inverse_transform the reference applies before measuring distances).
+ * scratch: pcfd_sdf_scratch_bytes(n_geom, n_points) bytes.
+ */
+int pcfd_sdf_feature(float* data, int32_t n_geom, int32_t n_points, int32_t f, int32_t n_internal, int32_t pos_col,
+                     int32_t dims, int32_t region_col, int32_t sdf_col, const float* coord_scale, float* scratch,
+                     void* stream);
+size_t pcfd_sdf_scratch_bytes(int32_t n_geom, int32_t n_points);
+/* FoamDataset.add_boundary_id (dataset/foam_dataset.py:382-395): columns col0 .. col0+n_classes-1 become zero for the
+ * internal rows and the one-hot class of the boundary rows; boundary_class [n_geom][n_points - n_internal] holds the
+ * position of each boundary row's patch name in the sorted list of patch names (what OneHotEncoder assigns). */
+int pcfd_boundary_one_hot(float* data, int32_t n_geom, int32_t n_points, int32_t f, int32_t n_internal,
+                          const int32_t* boundary_class, int32_t n_classes, int32_t col0, void* stream);
+/* collate_fn (dataset/foam_dataset.py:83-90) for a dataset resident in HBM: dst[i] = src[ids[i]] for n_ids blocks of
+ * block_bytes (a multiple of 4; 16-byte copies when everything is 16-byte aligned).  Used for the data tensor and for
+ * every sub-domain's row ids. */
+int pcfd_gather_blocks(const void* src, int64_t block_bytes, const int64_t* ids, int64_t n_ids, void* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

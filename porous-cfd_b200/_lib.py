@@ -77,6 +77,10 @@ SIGNATURES = {
     'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
     'pcfd_adam_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     'pcfd_relobralo_update': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F, _F, _F, _F, C.c_uint64, _P, _P]),
+    'pcfd_sdf_feature': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    'pcfd_sdf_scratch_bytes': (_SZ, [_I32, _I32]),
+    'pcfd_boundary_one_hot': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P]),
+    'pcfd_gather_blocks': (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     'pcfd_zero': (C.c_int, [_P, _I64, _P]),
     'pcfd_advance_seed': (C.c_int, [_P, _P]),
 }

@@ -377,5 +377,56 @@ def advance_seed(seed_dev: Tensor) -> None:
     check(lib.pcfd_advance_seed(seed_dev.data_ptr(), _stream()), 'pcfd_advance_seed')
 
 
+# ------------------------------------------------------------------------------------------------
+# batch ingestion on the device (csrc/ingest.cu; reference dataset/foam_dataset.py:83-90, 360-395)
+# ------------------------------------------------------------------------------------------------
+
+def sdf_feature(data: Tensor, n_internal: int, pos_col: int, dims: int, region_col: int, sdf_col: int,
+                coord_scale: Optional[Tensor] = None) -> None:
+    """In place: data (G, N, F)[..., sdf_col] = signed, max-normalised distance to the nearest boundary point."""
+    lib = _lib.load()
+    data = _f32(data, 'data')
+    if data.dim() != 3 or not data.is_contiguous():
+        raise _lib.PcfdError('sdf_feature: data must be a contiguous (G, N, F) tensor')
+    g, n, f = data.shape
+    if coord_scale is not None:
+        coord_scale = _f32(coord_scale, 'coord_scale').contiguous()
+        if coord_scale.numel() != dims:
+            raise _lib.PcfdError('sdf_feature: coord_scale needs one entry per dimension')
+    scratch = torch.empty(int(lib.pcfd_sdf_scratch_bytes(g, n)) // 4, dtype=torch.float32, device=data.device)
+    _lib.launches += 2
+    with _timed('sdf', 4.0 * g * n * (dims + 2)):
+      check(lib.pcfd_sdf_feature(data.data_ptr(), g, n, f, n_internal, pos_col, dims, region_col, sdf_col,
+                                 _ptr(coord_scale), scratch.data_ptr(), _stream()), 'pcfd_sdf_feature')
+
+
+def boundary_one_hot(data: Tensor, n_internal: int, boundary_class: Tensor, n_classes: int, col0: int) -> None:
+    """In place: data (G, N, F)[..., col0:col0+n_classes] = one-hot patch id of the boundary rows, zero inside."""
+    lib = _lib.load()
+    data = _f32(data, 'data')
+    g, n, f = data.shape
+    if not data.is_contiguous():
+        raise _lib.PcfdError('boundary_one_hot: data must be contiguous')
+    if boundary_class.dtype != torch.int32 or not boundary_class.is_cuda or tuple(boundary_class.shape) != (g, n - n_internal):
+        raise _lib.PcfdError('boundary_one_hot: boundary_class must be a CUDA int32 (G, N - n_internal) tensor')
+    _lib.launches += 1
+    check(lib.pcfd_boundary_one_hot(data.data_ptr(), g, n, f, n_internal, boundary_class.contiguous().data_ptr(),
+                                    n_classes, col0, _stream()), 'pcfd_boundary_one_hot')
+
+
+def gather_blocks(src: Tensor, ids: Tensor) -> Tensor:
+    """out[i] = src[ids[i]] along dimension 0 (collate of resident geometries); any 4- or 8-byte dtype."""
+    lib = _lib.load()
+    if not (src.is_cuda and ids.is_cuda) or ids.dtype != torch.int64 or not src.is_contiguous():
+        raise _lib.PcfdError('gather_blocks: src must be a contiguous CUDA tensor and ids a CUDA int64 tensor')
+    block_bytes = src[0].numel() * src.element_size()
+    out = torch.empty((ids.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    _lib.launches += 1
+    with _timed('collate', 2.0 * ids.numel() * block_bytes):
+      check(lib.pcfd_gather_blocks(src.data_ptr(), block_bytes, ids.contiguous().data_ptr(), ids.numel(), out.data_ptr(),
+                                   _stream()), 'pcfd_gather_blocks')
+    return out
+
+
 def set_gemm_engine(engine: int) -> None:
     check(_lib.load().pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')

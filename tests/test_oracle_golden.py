@@ -112,3 +112,43 @@ def test_relobralo_restatement_matches_reference_vectors(case):
     for s in range(int(steps)):
         got = sc(torch.from_numpy(z[f'{case}/losses'][s]))
         assert max_rel(got, torch.from_numpy(z[f'{case}/weighted'][s])) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side features of FoamDataset (dataset/foam_dataset.py:360-395): oracle/ingest_oracle.py against the vectors the
+# unmodified reference produced (tests/golden/make_ingest_golden.py)
+# ---------------------------------------------------------------------------------------------
+INGEST_CASES = ['abc3d', 'duct2d_minmax', 'std3d_ragged']
+
+
+@pytest.mark.parametrize('case', INGEST_CASES)
+def test_ingest_oracle_matches_reference_vectors(case):
+    import os
+    from oracle import ingest_oracle
+    z = np.load(os.path.join(GOLDEN, 'ingest.npz'))
+    scale = z[f'{case}/coord_scale'] if z[f'{case}/coord_scale'].size else None
+    si, sb = ingest_oracle.add_sdf(z[f'{case}/pos_internal'], z[f'{case}/pos_boundary'], z[f'{case}/region'], scale)
+    assert np.allclose(si, z[f'{case}/sdf_internal'], rtol=1e-12, atol=1e-15)
+    assert np.allclose(sb, z[f'{case}/sdf_boundary'], rtol=1e-12, atol=1e-15)
+    # properties the reference's construction implies: boundary points have distance 0 to themselves, the largest
+    # value is 1, porous-region points are negative
+    assert float(np.abs(sb).max()) == 0.0 and abs(float(np.abs(si).max()) - 1.0) < 1e-12
+    assert np.all(si[z[f'{case}/region'] > 0.5] <= 0) and np.all(si[z[f'{case}/region'] < 0.5] >= 0)
+    ni = len(si)
+    want = z[f'{case}/one_hot']
+    cls = z[f'{case}/boundary_class']
+    got = np.zeros_like(want)
+    got[ni + np.arange(len(cls)), cls] = 1.0
+    assert np.array_equal(got, want) and int(z[f'{case}/n_classes'][0]) == want.shape[1]
+
+
+def test_ingest_oracle_class_order_and_collate():
+    from oracle import ingest_oracle
+    cats, cls = ingest_oracle.boundary_classes(['walls', 'inlet', 'walls', 'interface'])
+    assert cats == ['inlet', 'interface', 'walls'] and cls.tolist() == [2, 0, 2, 1]
+    oh = ingest_oracle.boundary_one_hot(['b', 'a'], 2)
+    assert oh.tolist() == [[0, 0], [0, 0], [0, 1], [1, 0]]
+    datas = [np.full((3, 2), i, dtype=np.float32) for i in range(4)]
+    doms = [{'internal': np.arange(2) + i} for i in range(4)]
+    d, dom = ingest_oracle.collate(datas, doms)
+    assert d.shape == (4, 3, 2) and dom['internal'].tolist() == [[0, 1], [1, 2], [2, 3], [3, 4]]
