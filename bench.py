@@ -169,6 +169,48 @@ def _emit(line: dict):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + '\n').encode())
 
 
+def ingest_leg(dev_batches, labels, n_internal, dims, peaks):
+    """SURVEY 8f rank 4, outside the timed step: collation of HBM-resident geometries (pcfd_gather_blocks) and the
+    signed-distance feature (pcfd_sdf_feature) on this workload's shapes, CUDA events on the launching stream."""
+    from porous_cfd_b200.dataset.device_dataset import DeviceFoamDataset
+    b, n, f = dev_batches[0].data.shape
+    copies = max(1, int(160e6 // (len(dev_batches) * b * n * f * 4)) + 1)        # resident set larger than the 126 MB L2
+    data = torch.cat([d.data for d in dev_batches] * copies)
+    domain = {k: torch.cat([d.domain[k] for d in dev_batches] * copies) for k in dev_batches[0].domain}
+    ds = DeviceFoamDataset(data, labels, domain)
+    gen = torch.Generator().manual_seed(0)
+    ids = [torch.randperm(len(ds), generator=gen)[:b].cuda() for _ in range(8)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(3):
+        ds.batch(ids[i])
+    ev[0].record()
+    for i in range(24):
+        ds.batch(ids[i % 8])
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms_collate = ev[0].elapsed_time(ev[1]) / 24
+    nbytes = 2.0 * (b * n * f * 4 + sum(v.shape[1] for v in domain.values()) * b * 8)
+    sub = DeviceFoamDataset(dev_batches[0].data.clone(), labels, dev_batches[0].domain)
+    for _ in range(2):
+        sub.add_sdf()
+    ev[0].record()
+    for _ in range(5):
+        sub.add_sdf()
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms_sdf = ev[0].elapsed_time(ev[1]) / 5
+    pairs = float(b) * n * (n - n_internal)
+    return {'resident_geometries': len(ds), 'resident_mb': data.numel() * 4 / 1e6,
+            'collate': {'ms_per_batch': ms_collate, 'gbs': nbytes / (ms_collate / 1e3) / 1e9,
+                        'frac_of_hbm_peak': nbytes / (ms_collate / 1e3) / 1e9 / peaks['hbm_gbs'],
+                        'bytes': 'read + write of the batch tensor and every sub-domain id tensor',
+                        'note': 'one launch per batch; a batch is a few MB, so this loop is bounded by the host-side '
+                                'dispatch (output allocations + one ctypes call), not by HBM; it replaces the '
+                                'host-to-device copy of the same bytes'},
+            'sdf': {'ms_per_batch': ms_sdf, 'geometries': b, 'distance_pairs_per_s': pairs / (ms_sdf / 1e3),
+                    'bound': 'fp32 FMA (n x n_boundary distance evaluations per geometry)'}}
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -422,6 +464,10 @@ def main():
     if 'fps' in fam:
         roofline['fps'] = {'ms_per_launch': fam['fps']['ms'] / fam['fps']['launches'], 'note': 'latency-bound (sequential sampling)'}
 
+    ingest = None
+    if world == 1:
+        ingest = ingest_leg(dev_batches, labels, SHAPE['n_internal'], spec['dims'], peaks)
+
     cpu = None
     if not args.no_cpu_baseline:
         pts, ms_cpu, threads = cpu_reference_step_rate(steps=6, warmup=2, n_geom=2)
@@ -440,7 +486,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'ms_per_step': ms_e2e / K, 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); '
                            'FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]'},
-            'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu}
+            'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu, 'ingest': ingest}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

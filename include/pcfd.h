@@ -297,6 +297,12 @@ int pcfd_boundary_one_hot(float* data, int32_t n_geom, int32_t n_points, int32_t
  * block_bytes (a multiple of 4; 16-byte copies when everything is 16-byte aligned).  Used for the data tensor and for
  * every sub-domain's row ids. */
 int pcfd_gather_blocks(const void* src, int64_t block_bytes, const int64_t* ids, int64_t n_ids, void* dst, void* stream);
+/* The same for up to PCFD_GATHER_MAX_TENSORS tensors of one dataset in ONE launch (the data tensor and the row ids of
+ * every sub-domain): dst[t][i] = src[t][ids[i]].  The three arrays are host arrays read at call time; ids is a device
+ * array; a block size of 0 (an empty sub-domain) is skipped. */
+#define PCFD_GATHER_MAX_TENSORS 16
+int pcfd_gather_blocks_multi(const void* const* src_host, void* const* dst_host, const int64_t* block_bytes_host,
+                             int32_t n_tensors, const int64_t* ids, int64_t n_ids, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,7 @@ SIGNATURES = {
     'pcfd_sdf_scratch_bytes': (_SZ, [_I32, _I32]),
     'pcfd_boundary_one_hot': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P]),
     'pcfd_gather_blocks': (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
+    'pcfd_gather_blocks_multi': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I32, _P, _I64, _P]),
     'pcfd_zero': (C.c_int, [_P, _I64, _P]),
     'pcfd_advance_seed': (C.c_int, [_P, _P]),
 }

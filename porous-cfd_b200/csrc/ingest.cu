@@ -97,6 +97,29 @@ __global__ void __launch_bounds__(256) gather_blocks_kernel(const T* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < block_elems; i += (int64_t)gridDim.x * 256) d[i] = __ldg(s + i);
 }
 
+// several tensors of the same dataset (data + every sub-domain's ids) in one launch: blockIdx.z = tensor
+struct GatherTable {
+  const void* src[PCFD_GATHER_MAX_TENSORS];
+  void* dst[PCFD_GATHER_MAX_TENSORS];
+  int64_t elems[PCFD_GATHER_MAX_TENSORS];      // per block, in units of 16 bytes (vec) or 4 bytes
+  int vec[PCFD_GATHER_MAX_TENSORS];
+};
+
+__global__ void __launch_bounds__(256) gather_blocks_multi_kernel(const __grid_constant__ GatherTable t,
+                                                                  const int64_t* __restrict__ ids) {
+  const int k = blockIdx.z;
+  const int64_t b = blockIdx.y, id = __ldg(ids + b), n = t.elems[k];
+  if (t.vec[k]) {
+    const uint4* s = reinterpret_cast<const uint4*>(t.src[k]) + id * n;
+    uint4* d = reinterpret_cast<uint4*>(t.dst[k]) + b * n;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) d[i] = __ldg(s + i);
+  } else {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(t.src[k]) + id * n;
+    uint32_t* d = reinterpret_cast<uint32_t*>(t.dst[k]) + b * n;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) d[i] = __ldg(s + i);
+  }
+}
+
 }  // namespace pcfd
 
 using namespace pcfd;
@@ -112,12 +135,16 @@ extern "C" int pcfd_sdf_feature(float* data, int32_t n_geom, int32_t n_points, i
   float* dist = scratch;
   unsigned* gmax = reinterpret_cast<unsigned*>(scratch + (int64_t)n_geom * n_points);
   if (cudaMemsetAsync(gmax, 0, sizeof(unsigned) * n_geom, st) != cudaSuccess) return PCFD_ERR_CUDA;
-  dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)n_geom);
-  if (dims == 2) sdf_min_kernel<2><<<grid, 256, 0, st>>>(data, f, pos_col, n_points, n_internal, coord_scale, dist, gmax);
-  else sdf_min_kernel<3><<<grid, 256, 0, st>>>(data, f, pos_col, n_points, n_internal, coord_scale, dist, gmax);
-  PCFD_CHECK_LAUNCH();
-  sdf_finish_kernel<<<grid, 256, 0, st>>>(data, f, sdf_col, region_col, n_points, n_internal, dist, gmax);
-  PCFD_CHECK_LAUNCH();
+  for (int32_t g0 = 0; g0 < n_geom; g0 += 65535) {             // grid.y limit
+    const int32_t ng = n_geom - g0 < 65535 ? n_geom - g0 : 65535;
+    float* d0 = data + (int64_t)g0 * n_points * f;
+    dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)ng);
+    if (dims == 2) sdf_min_kernel<2><<<grid, 256, 0, st>>>(d0, f, pos_col, n_points, n_internal, coord_scale, dist + (int64_t)g0 * n_points, gmax + g0);
+    else sdf_min_kernel<3><<<grid, 256, 0, st>>>(d0, f, pos_col, n_points, n_internal, coord_scale, dist + (int64_t)g0 * n_points, gmax + g0);
+    PCFD_CHECK_LAUNCH();
+    sdf_finish_kernel<<<grid, 256, 0, st>>>(d0, f, sdf_col, region_col, n_points, n_internal, dist + (int64_t)g0 * n_points, gmax + g0);
+    PCFD_CHECK_LAUNCH();
+  }
   return PCFD_OK;
 }
 
@@ -129,9 +156,13 @@ extern "C" int pcfd_boundary_one_hot(float* data, int32_t n_geom, int32_t n_poin
                                      const int32_t* boundary_class, int32_t n_classes, int32_t col0, void* stream) {
   if (!data || !boundary_class || n_geom <= 0 || n_points <= 0 || n_internal < 0 || n_internal > n_points) return PCFD_ERR_ARG;
   if (n_classes <= 0 || col0 < 0 || col0 + n_classes > f) return PCFD_ERR_ARG;
-  dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)n_geom);
-  one_hot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data, f, col0, n_classes, n_points, n_internal, boundary_class);
-  PCFD_CHECK_LAUNCH();
+  for (int32_t g0 = 0; g0 < n_geom; g0 += 65535) {             // grid.y limit
+    const int32_t ng = n_geom - g0 < 65535 ? n_geom - g0 : 65535;
+    dim3 grid((unsigned)((n_points + 255) / 256), (unsigned)ng);
+    one_hot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(data + (int64_t)g0 * n_points * f, f, col0, n_classes, n_points,
+                                                           n_internal, boundary_class + (int64_t)g0 * (n_points - n_internal));
+    PCFD_CHECK_LAUNCH();
+  }
   return PCFD_OK;
 }
 
@@ -151,6 +182,37 @@ extern "C" int pcfd_gather_blocks(const void* src, int64_t block_bytes, const in
   dim3 grid((unsigned)per, (unsigned)n_ids);
   if (v16) gather_blocks_kernel<uint4><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), elems, ids, reinterpret_cast<uint4*>(dst));
   else gather_blocks_kernel<uint32_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(src), elems, ids, reinterpret_cast<uint32_t*>(dst));
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
+extern "C" int pcfd_gather_blocks_multi(const void* const* src_host, void* const* dst_host, const int64_t* block_bytes_host,
+                                        int32_t n_tensors, const int64_t* ids, int64_t n_ids, void* stream) {
+  if (!src_host || !dst_host || !block_bytes_host || !ids || n_tensors <= 0 || n_tensors > PCFD_GATHER_MAX_TENSORS)
+    return PCFD_ERR_ARG;
+  if (n_ids < 0 || n_ids > 65535) return PCFD_ERR_ARG;
+  GatherTable t;
+  int m = 0;
+  int64_t largest = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    const int64_t bytes = block_bytes_host[i];
+    if (bytes < 0 || bytes % 4) return PCFD_ERR_ARG;
+    if (bytes == 0) continue;                                   // an empty sub-domain (no observation points)
+    if (!src_host[i] || !dst_host[i]) return PCFD_ERR_ARG;
+    const bool v16 = bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src_host[i]) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dst_host[i]) & 15) == 0;
+    t.src[m] = src_host[i]; t.dst[m] = dst_host[i]; t.vec[m] = v16 ? 1 : 0;
+    t.elems[m] = v16 ? bytes / 16 : bytes / 4;
+    if (t.elems[m] > largest) largest = t.elems[m];
+    ++m;
+  }
+  if (m == 0 || n_ids == 0) return PCFD_OK;
+  int64_t per = (largest + 256 * 4 - 1) / (256 * 4);
+  const int64_t want = (148 * 8 + n_ids - 1) / n_ids;
+  if (per > want) per = want;
+  if (per < 1) per = 1;
+  dim3 grid((unsigned)per, (unsigned)n_ids, (unsigned)m);
+  gather_blocks_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, ids);
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
 }

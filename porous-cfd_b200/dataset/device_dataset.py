@@ -72,13 +72,20 @@ class DeviceFoamDataset:
         ops.boundary_one_hot(self.data, self._n_internal(), cls, len(cols), cols[0])
 
     # ---- batches (reference: collate_fn) -----------------------------------------------------------------------
+    def _gather(self, ids: Tensor) -> FoamData:
+        names = list(self.domain)
+        out = ops.gather_blocks_multi([self.data] + [self.domain[k] for k in names], ids)     # one launch
+        return FoamData(out[0], self.labels, dict(zip(names, out[1:])))
+
     def batch(self, geometry_ids) -> FoamData:
-        ids = torch.as_tensor(geometry_ids, dtype=torch.int64).to(self.data.device)
+        """collate_fn of the chosen geometries.  Ids given on the host are range-checked; a CUDA id tensor is used as
+        it is (checking it would cost a device synchronisation per batch)."""
+        if torch.is_tensor(geometry_ids) and geometry_ids.is_cuda:
+            return self._gather(geometry_ids.to(torch.int64))
+        ids = torch.as_tensor(geometry_ids, dtype=torch.int64)
         if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= len(self)):
             raise IndexError('geometry id out of range')
-        data = ops.gather_blocks(self.data, ids)
-        domain = {k: ops.gather_blocks(v, ids) for k, v in self.domain.items()}
-        return FoamData(data, self.labels, domain)
+        return self._gather(ids.to(self.data.device))
 
     def batches(self, batch_size: int, shuffle: bool = True, generator: Optional[torch.Generator] = None,
                 drop_last: bool = False):
@@ -90,5 +97,4 @@ class DeviceFoamDataset:
             ids = order[lo:lo + batch_size]
             if drop_last and ids.numel() < batch_size:
                 return
-            data = ops.gather_blocks(self.data, ids)
-            yield FoamData(data, self.labels, {k: ops.gather_blocks(v, ids) for k, v in self.domain.items()})
+            yield self._gather(ids)

@@ -428,5 +428,28 @@ def gather_blocks(src: Tensor, ids: Tensor) -> Tensor:
     return out
 
 
+def gather_blocks_multi(srcs, ids: Tensor) -> list:
+    """[src[ids] for src in srcs] along dimension 0 in one launch (at most 16 tensors; empty blocks allowed)."""
+    lib = _lib.load()
+    if ids.dtype != torch.int64 or not ids.is_cuda:
+        raise _lib.PcfdError('gather_blocks_multi: ids must be a CUDA int64 tensor')
+    ids = ids.contiguous()
+    outs, nbytes = [], []
+    for src in srcs:
+        if not src.is_cuda or not src.is_contiguous():
+            raise _lib.PcfdError('gather_blocks_multi: sources must be contiguous CUDA tensors')
+        outs.append(torch.empty((ids.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device))
+        nbytes.append(src[0].numel() * src.element_size() if src.shape[0] else 0)
+    n = len(srcs)
+    src_arr = (C.c_void_p * n)(*[s.data_ptr() for s in srcs])
+    dst_arr = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    len_arr = (C.c_int64 * n)(*nbytes)
+    _lib.launches += 1
+    with _timed('collate', 2.0 * ids.numel() * sum(nbytes)):
+      check(lib.pcfd_gather_blocks_multi(src_arr, dst_arr, len_arr, n, ids.data_ptr(), ids.numel(), _stream()),
+            'pcfd_gather_blocks_multi')
+    return outs
+
+
 def set_gemm_engine(engine: int) -> None:
     check(_lib.load().pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')

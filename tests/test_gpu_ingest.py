@@ -68,9 +68,18 @@ def test_sdf_many_geometries_against_oracle():
         assert abs(float(np.abs(got).max()) - 1.0) < 1e-6 and float(np.abs(got[ni:]).max()) == 0.0
 
 
-@pytest.mark.parametrize('layout', ['abc', 'duct_variable', 'manufactured'])
-def test_device_collate_is_bit_exact(layout):
-    data, labels, domain = synthetic.make_batch(layout, n_geometries=7, n_internal=150, n_boundary=101, n_obs=33, seed=11)
+def test_gather_blocks_single_tensor():
+    from porous_cfd_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    ids = torch.tensor([5, 0, 5, 2], device='cuda')
+    for shape, dtype in (((6, 37, 3), torch.float32), ((6, 16, 8), torch.float32), ((6, 9), torch.int64)):
+        src = (torch.rand(shape, generator=gen) * 100).to(dtype).cuda()
+        assert torch.equal(ops.gather_blocks(src, ids), src[ids])
+
+
+@pytest.mark.parametrize('layout,n_obs', [('abc', 33), ('duct_variable', 33), ('manufactured', 0)])
+def test_device_collate_is_bit_exact(layout, n_obs):
+    data, labels, domain = synthetic.make_batch(layout, n_geometries=7, n_internal=150, n_boundary=101, n_obs=n_obs, seed=11)
     samples = [FoamData(data[i], labels, {k: v[i] for k, v in domain.items()}) for i in range(7)]
     ds = DeviceFoamDataset.from_samples(samples)
     assert len(ds) == 7
@@ -86,6 +95,8 @@ def test_device_collate_is_bit_exact(layout):
     assert sorted(seen.tolist()) == sorted(data[:, 0, 0].tolist())
     with pytest.raises(IndexError):
         ds.batch([7])
+    dev_ids = torch.tensor([2, 5], device='cuda')                    # ids already on the device: no host round trip
+    assert torch.equal(ds.batch(dev_ids).data.cpu(), data[[2, 5]])
 
 
 def test_training_step_from_a_device_batch():
