@@ -222,6 +222,8 @@ def main():
                     help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 1 = tcgen05 with thread-staged operands, 0 = fp32 FFMA')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-pipeline', action='store_true',
+                    help='compute the set-abstraction geometry (FPS, ball query) of a batch inside its own step instead of one step ahead')
     ap.add_argument('--laplacian', default='reference', choices=['reference', 'true'])
     ap.add_argument('--config', default='abc_pipn_pp', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='geometries per GPU (default: the config\'s own)')
@@ -283,10 +285,13 @@ def main():
     static = FoamData(torch.empty_like(dev_batches[0].data), labels,
                       {k: torch.empty_like(v) for k, v in dev_batches[0].domain.items()})
 
-    def load_static(src: FoamData):
-        static.data.copy_(src.data, non_blocking=True)
+    pipelined = (not args.no_pipeline) and (not args.no_graph) and ex.uses_geometry()
+    geo = None
+
+    def load_static(src: FoamData, dst: FoamData = static):
+        dst.data.copy_(src.data, non_blocking=True)
         for k, v in src.domain.items():
-            static.domain[k].copy_(v, non_blocking=True)
+            dst.domain[k].copy_(v, non_blocking=True)
 
     def eager_step(batch):
         return trainer.train_step(batch, args.laplacian)
@@ -309,11 +314,28 @@ def main():
                         trainer.step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            if pipelined:
+                # geometry of the NEXT batch (positions only: FPS, ball query, edge slots) as an independent branch of
+                # the graph; this batch's geometry sits in static buffers filled by the previous replay
+                geo = ex.geometry(static.data, labels, static.domain)
+                pos_next = ex.geometry_positions(dev_batches[1 % N_BATCHES].data, labels, dev_batches[1 % N_BATCHES].domain)
+                geo_side = torch.cuda.Stream()
+                torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                graph_res = model.fused_step(static, args.laplacian)
+                if pipelined:
+                    cap = torch.cuda.current_stream()
+                    geo_side.wait_stream(cap)
+                    with torch.cuda.stream(geo_side):
+                        geo_next = ex.geometry(None, labels, None, pos=pos_next)
+                graph_res = model.fused_step(static, args.laplacian, geo=geo)
                 if world == 1:
                     trainer.step()      # fused Adam on the flat buffers, inside the graph (no collective at N = 1)
+                if pipelined:
+                    cap.wait_stream(geo_side)
+                    for cur_l, new_l in zip(geo, geo_next):
+                        for gk in cur_l:
+                            cur_l[gk].copy_(new_l[gk])
         except Exception as e:  # report and fall back to per-kernel launches (still the CUDA path)
             if rank == 0:
                 print(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); launching eagerly', file=sys.stderr)
@@ -323,6 +345,9 @@ def main():
     def step(i):
         if graph is not None:
             load_static(dev_batches[i % N_BATCHES])
+            if pipelined:      # the geometry branch reads only the sampled positions of the next batch: one gather launch
+                nb_ = dev_batches[(i + 1) % N_BATCHES]
+                ex.geometry_positions(nb_.data, labels, nb_.domain, out=pos_next)
             graph.replay()
             if world > 1:
                 trainer.reduce_gradients()
@@ -363,17 +388,28 @@ def main():
             ev.record(copy_stream)
         return b, ev
 
-    pending = {'next': prefetch(0)}
+    model.pipeline_geometry = pipelined
+    # with the geometry pipeline the graph of step i also reads the positions of batch i+1, so the copy of batch i+1
+    # was issued during step i-1 and this step issues the copy of batch i+2: still one batch copied per step
+    depth = 2 if pipelined else 1
+    pending = {'queue': [prefetch(j) for j in range(depth)]}
 
     def e2e_step(i):
-        batch, ev = pending['next']
+        batch, ev = pending['queue'].pop(0)
         cur = torch.cuda.current_stream()
         cur.wait_event(ev)
         batch.data.record_stream(cur)
         for v in batch.domain.values():
             v.record_stream(cur)
+        if pipelined:
+            nxt, nev = pending['queue'][0]
+            cur.wait_event(nev)
+            nxt.data.record_stream(cur)
+            for v in nxt.domain.values():
+                v.record_stream(cur)
+            model.announce_next_batch(nxt)
         loss = model.training_step(batch, i)
-        pending['next'] = prefetch(i + 1)         # issued once this step's graph is enqueued: off the launch critical path
+        pending['queue'].append(prefetch(i + depth))   # issued once this step's graph is enqueued: off the launch critical path
         for p in params:
             p.grad = None
         loss.backward()
@@ -481,6 +517,8 @@ def main():
                                    f'{B_PER_GPU} geometries per GPU', 'global_batch': world * B_PER_GPU,
                        'laplacian': args.laplacian, 'dropout': 'on', 'optimizer': 'fused Adam in the step',
                        'parallelism': f'dp{world}', 'cuda_graph': graph is not None,
+                       'geometry': ('FPS / ball query of batch t+1 run as a parallel branch of step t (positions only; '
+                                    'one batch worth per step)') if pipelined else 'inside the step',
                        'l2': 'per-step working set (jets + gradients ~1 GB) exceeds the 126 MB L2; 4 batches cycled, no flush'},
             'loss': loss_value, 'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'ms_per_step': ms_e2e / K, 'h2d_bytes_per_step': h2d_bytes,

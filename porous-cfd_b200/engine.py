@@ -154,22 +154,39 @@ class SAStack:
     out_features: int = 0
 
 
-def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int, pos0: Tensor):
-    """x0 [B*n0, ldx0] features, pos0 (B, n0, D) -> (g [B, ld] pooled feature, saved state)."""
+def sa_geometry(stack: SAStack, pos0: Tensor) -> list:
+    """The part of the set-abstraction stack that depends on the point positions only (no weights, no features):
+    per level the FPS centroids, the radius neighbourhoods as edge slots, and the centroid positions.  A training loop
+    that knows its next batch can run this for batch t+1 beside the step of batch t (PinnExecutor.geometry)."""
     b, n, d = pos0.shape
-    x, ldx, f, pos = x0, ldx0, f0, pos0
-    saved = {'levels': [], 'b': b, 'd': d}
+    pos, geo = pos0, []
     for lvl in stack.levels:
         idx = ops.fps(pos, lvl.ratio)
         m = idx.shape[1]
         nbr, _ = ops.ball_query(pos, idx, lvl.radius, lvl.max_neighbors)
         slots = ops.sa_edges(nbr, b * n)
+        newpos = torch.empty((b, m, d), dtype=torch.float32, device=pos.device)
+        ops.gather_cols(pos, 1, b * n, d, idx, 0, b * m, list(range(d)), newpos, d, b * m)
+        geo.append({'idx': idx, 'slots': slots, 'newpos': newpos})
+        pos, n = newpos, m
+    return geo
+
+
+def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int, pos0: Tensor, geo: Optional[list] = None):
+    """x0 [B*n0, ldx0] features, pos0 (B, n0, D) -> (g [B, ld] pooled feature, saved state).  `geo`: the output of
+    sa_geometry(stack, pos0) when it was computed ahead of the step."""
+    b, n, d = pos0.shape
+    x, ldx, f, pos = x0, ldx0, f0, pos0
+    saved = {'levels': [], 'b': b, 'd': d}
+    if geo is None:
+        geo = sa_geometry(stack, pos0)
+    for lvl, gl in zip(stack.levels, geo):
+        idx, slots, newpos = gl['idx'], gl['slots'], gl['newpos']
+        m = idx.shape[1]
         ein = ops.sa_gather(x, ldx, f, pos, idx, slots, lvl.radius)
         zs = chain_forward(ctx, lvl.layers, Jet(ein, f + d), 0)
         c = lvl.layers[-1].n
         out, arg = ops.segmax_fwd(zs[-1].t[0], lvl.act, slots, b * m, slots.shape[1], c)
-        newpos = torch.empty((b, m, d), dtype=torch.float32, device=pos.device)
-        ops.gather_cols(pos, 1, b * n, d, idx, 0, b * m, list(range(d)), newpos, d, b * m)
         saved['levels'].append({'slots': slots, 'zs': zs, 'arg': arg, 'm': m, 'n': n, 'f_in': f, 'ldx': ldx, 'c': c})
         x, ldx, f, pos, n = out, out.stride(0), c, newpos, m
     if stack.global_layers is None:
@@ -236,25 +253,67 @@ class StepResult:
 class GraphedStep:
     """One captured CUDA graph of `PinnExecutor.step` for a fixed input signature.  Inputs are copied into static
     device buffers (device-to-device, a few microseconds), the ~130 kernels of the step replay as one launch, and the
-    results live in static buffers that stay valid until the next replay."""
+    results live in static buffers that stay valid until the next replay.
 
-    def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str):
+    With `pipeline=True` (models with a set-abstraction encoder) the graph holds a second, independent branch: the
+    geometry (FPS, ball query, edge slots) of the NEXT batch, which depends on positions only.  FPS is a sequential
+    chain on one CTA per geometry at the very head of the step; computed one step ahead it runs beside the previous
+    step's GEMMs instead.  Every replay still does one full step worth of work (geometry of one batch + the rest of
+    another).  `run(..., next_data, next_domain)` names the batch the following call will bring; a call whose batch was
+    not announced computes its geometry in line first."""
+
+    def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str, pipeline: bool = False):
+        self.ex = ex
         self.data = torch.empty_like(data)
         self.domain = {k: torch.empty_like(v) for k, v in domain.items()}
         self.labels = labels
+        self.pipeline = pipeline and ex.uses_geometry()
         self.load(data, domain)
+        self.geo = None
+        self.expected = None          # signature of the batch whose geometry the static buffers hold
+        if self.pipeline:
+            # the only input of the geometry branch: the next batch's sampled positions, gathered into a static buffer
+            self.pos_next = ex.geometry_positions(self.data, labels, self.domain)
+            self.geo = ex.geometry(self.data, labels, self.domain)          # static buffers, filled for this first batch
+            self.geo_side = torch.cuda.Stream(device=data.device)
         torch.cuda.current_stream().synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.result = ex.step(self.data, labels, self.domain, laplacian)
+            if self.pipeline:
+                main = torch.cuda.current_stream()
+                self.geo_side.wait_stream(main)
+                with torch.cuda.stream(self.geo_side):
+                    nxt = ex.geometry(None, labels, None, pos=self.pos_next)
+                self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
+                main.wait_stream(self.geo_side)
+                for cur, new in zip(self.geo, nxt):                          # after the step's last use of the old ones
+                    for k in cur:
+                        cur[k].copy_(new[k])
+            else:
+                self.result = ex.step(self.data, labels, self.domain, laplacian)
+
+    @staticmethod
+    def _sig(data: Tensor):
+        return (data.data_ptr(), data._version, tuple(data.shape))
 
     def load(self, data: Tensor, domain: dict) -> None:
         self.data.copy_(data, non_blocking=True)
         for k, v in domain.items():
             self.domain[k].copy_(v, non_blocking=True)
 
-    def run(self, data: Tensor, domain: dict) -> 'StepResult':
+    def run(self, data: Tensor, domain: dict, next_data: Optional[Tensor] = None, next_domain: Optional[dict] = None) -> 'StepResult':
         self.load(data, domain)
+        if self.pipeline:
+            if self.expected != self._sig(data):
+                # not announced by the previous call: geometry of this batch in line, into the static buffers
+                fresh = self.ex.geometry(self.data, self.labels, self.domain)
+                for cur, new in zip(self.geo, fresh):
+                    for k in cur:
+                        cur[k].copy_(new[k])
+            if next_data is None:
+                next_data, next_domain = data, domain
+            self.ex.geometry_positions(next_data, self.labels, next_domain, out=self.pos_next)     # one launch
+            self.expected = self._sig(next_data)
         self.graph.replay()
         return self.result
 
@@ -265,7 +324,7 @@ class _EagerStep:
     def __init__(self, ex, labels, laplacian):
         self.ex, self.labels, self.laplacian = ex, labels, laplacian
 
-    def run(self, data, domain):
+    def run(self, data, domain, next_data=None, next_domain=None):
         return self.ex.step(data, self.labels, domain, self.laplacian)
 
 
@@ -318,9 +377,10 @@ class PinnExecutor:
                               side=ctx.side_stream if ctx.overlap else None)
 
     # ---- encode: per-geometry constants ------------------------------------------------------
-    def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor]):
+    def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor],
+                geo: Optional[list] = None):
         """Returns (cvecs, escale, saved).  `points` (B,N,D) overrides the coordinates taken from
-        `data` (used by forward(autograd_points, x))."""
+        `data` (used by forward(autograd_points, x)).  `geo`: set-abstraction geometry computed ahead (self.geometry)."""
         plan, ctx = self.plan, self.ctx
         b, n_rows, f = data.shape
         d = plan['dims']
@@ -338,7 +398,7 @@ class PinnExecutor:
                 gcols += self._cols(labels, name)
             x0 = torch.empty((b * nb, ops.round4(len(gcols))), dtype=torch.float32, device=data.device)
             self._gather(data, bnd_ids, nb, gcols, x0, x0.stride(0), nb)
-            g, sa_saved = sa_forward(ctx, plan['sa_stack'], x0, x0.stride(0), len(gcols), pos)
+            g, sa_saved = sa_forward(ctx, plan['sa_stack'], x0, x0.stride(0), len(gcols), pos, geo)
             saved['sa'] = sa_saved
             gfeat, gwidth = g, plan['sa_stack'].global_layers[-1].n
         elif fam == 'pigano':
@@ -456,20 +516,26 @@ class PinnExecutor:
         ops.end_step()
         return zs[-1].values().reshape(b, n, d + 1)
 
-    def graphed_step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference') -> StepResult:
+    def graphed_step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
+                     next_batch=None) -> StepResult:
         """`step` replayed from a CUDA graph.  The first call with a given signature runs eagerly (it sizes the
         workspace and the padded weight copies), the second captures, later ones replay; every call is exactly one
         training step (dropout seed, ReLoBRaLo state and gradients advance once)."""
         key = (tuple(data.shape), tuple((k, tuple(v.shape)) for k, v in sorted(domain.items())), tuple(labels),
                laplacian, self.model.training, self.model.enable_data_loss)
+        pipeline = bool(getattr(self.model, 'pipeline_geometry', False))
+        key = key + (pipeline,)
+        nd, ndom = (next_batch.data, next_batch.domain) if next_batch is not None else (None, None)
+        if nd is not None and (tuple(nd.shape) != tuple(data.shape) or any(tuple(ndom[k].shape) != tuple(v.shape) for k, v in domain.items())):
+            nd, ndom = None, None        # a differently shaped next batch (last, smaller one) cannot share the buffers
         g = self._graphs.get(key)
         if g is not None:
-            return g.run(data, domain)
+            return g.run(data, domain, nd, ndom)
         if key not in self._seen:
             self._seen.add(key)
             return self.step(data, labels, domain, laplacian)
         try:
-            g = GraphedStep(self, data, labels, domain, laplacian)
+            g = GraphedStep(self, data, labels, domain, laplacian, pipeline)
         except RuntimeError as exc:      # an op that cannot be captured: stay on the per-kernel launches for this signature
             import warnings
             warnings.warn(f'CUDA graph capture of the fused step failed ({exc}); launching eagerly')
@@ -478,8 +544,7 @@ class PinnExecutor:
             self._graphs[key] = _EagerStep(self, labels, laplacian)
             return self._graphs[key].run(data, domain)
         self._graphs[key] = g
-        g.graph.replay()
-        return g.result
+        return g.run(data, domain, nd, ndom)
 
     def predict_with_residuals(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference'):
         """predict_step(verbose): predictions at all points (B, N, D+1) and the residual map of the internal
@@ -505,8 +570,31 @@ class PinnExecutor:
         pred = torch.cat([y_int.values().reshape(b, ni, d + 1), y_bnd.values().reshape(b, nb, d + 1)], dim=1)
         return pred, fields
 
+    def uses_geometry(self) -> bool:
+        """True for the models with a set-abstraction encoder (FPS / ball query in front of the step)."""
+        return self.plan['family'] in ('pipn_pp', 'pigano_pp')
+
+    def geometry_positions(self, data: Tensor, labels: dict, domain: dict, out: Optional[Tensor] = None) -> Tensor:
+        """(B, n_boundary, D) coordinates of the points the set-abstraction encoder samples (one gather launch)."""
+        b = data.shape[0]
+        d = self.plan['dims']
+        bnd_ids = domain['boundary']
+        nb = bnd_ids.shape[1]
+        pos = out if out is not None else torch.empty((b, nb, d), dtype=torch.float32, device=data.device)
+        self._gather(data, bnd_ids, nb, self._cols(labels, 'C'), pos, d, nb)
+        return pos
+
+    def geometry(self, data: Tensor, labels: dict, domain: dict, pos: Optional[Tensor] = None) -> Optional[list]:
+        """The weight-independent head of the encoder for a batch: FPS centroids, neighbourhood slots and centroid
+        positions of every set-abstraction level (sa_geometry).  Pass the result to `step(..., geo=...)`."""
+        if not self.uses_geometry():
+            return None
+        if pos is None:
+            pos = self.geometry_positions(data, labels, domain)
+        return sa_geometry(self.plan['sa_stack'], pos)
+
     def step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
-             keep_outputs: bool = False) -> StepResult:
+             keep_outputs: bool = False, geo: Optional[list] = None) -> StepResult:
         """One fused training step: fills the flat gradient buffer and returns the loss vector."""
         plan, ctx = self.plan, self.ctx
         model = self.model
@@ -543,7 +631,7 @@ class PinnExecutor:
             z0_bnd = ops.seed_jet(data, bnd_ids, nb, c_cols, 1)
             zs_int = chain_forward(ctx, layers[:n_pre], z0_int, ni, None, None, salt_base=100)
             zs_bnd = chain_forward(ctx, layers[:n_pre], z0_bnd, nb, None, None, salt_base=200)
-        cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None)
+        cvecs, escale, saved = self._encode(data, labels, domain, int_ids, bnd_ids, None, geo)
         main.wait_stream(side)
         # the boundary chain (value only, small grids) fills the gaps of the internal chain from the side stream
         side.wait_stream(main)

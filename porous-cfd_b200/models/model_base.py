@@ -73,6 +73,8 @@ class PorousPinnBase(_Base):
         super().__init__()
         self.verbose_predict = False
         self.cuda_graph = False        # training_step replays the fused step from a CUDA graph (per input signature)
+        self.pipeline_geometry = False  # with cuda_graph: FPS / ball query of the announced next batch run beside this step
+        self._next_batch = None
         self.enable_data_loss = bool(enable_data_loss)
         self.dims = out_features - 1
         self.laplacian = laplacian
@@ -176,13 +178,20 @@ class PorousPinnBase(_Base):
         y = self.executor.forward_values(autograd_points, x.data, x.labels, x.domain)
         return FoamData(y, self.predicted_labels, x.domain)
 
-    def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False):
-        """The hot path without the autograd wrapper: fills `executor.flat_grad`, returns StepResult."""
-        return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs)
+    def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False, geo=None):
+        """The hot path without the autograd wrapper: fills `executor.flat_grad`, returns StepResult.  `geo`: the
+        batch's set-abstraction geometry when it was computed ahead (`executor.geometry`)."""
+        return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs, geo)
+
+    def announce_next_batch(self, batch: Optional[FoamData]) -> None:
+        """Optional hint for `pipeline_geometry`: the batch the NEXT training_step call will receive (already on the
+        device).  Its set-abstraction geometry is then computed inside this step's graph, off the critical path."""
+        self._next_batch = batch
 
     def training_step(self, batch: FoamData, batch_idx: int = 0):
         if self.cuda_graph:
-            res = self.executor.graphed_step(batch.data, batch.labels, batch.domain, self.laplacian)
+            nxt, self._next_batch = self._next_batch, None
+            res = self.executor.graphed_step(batch.data, batch.labels, batch.domain, self.laplacian, next_batch=nxt)
         else:
             res = self.fused_step(batch)
         self.last_step = res

@@ -310,3 +310,38 @@ def test_cuda_graph_training_step_equals_eager():
         g1 = {k: p.grad for k, p in graphed.named_parameters()}
         assert rel_l2(flat(g1, keys), flat(g0, keys)) < 1e-6, step
     assert len(graphed.executor._graphs) == 1
+
+
+@pytest.mark.parametrize('name', ['tiny_pipn_pp', 'tiny_pigano_pp'])
+def test_pipelined_geometry_equals_eager(name):
+    """model.pipeline_geometry: FPS / ball query of the announced next batch run inside the current step's graph.
+    Losses and gradients equal the eager path for announced batches, for a batch that was NOT announced (its geometry is
+    then computed in line), and for a wrong announcement."""
+    spec = synthetic.model_spec(name)
+    _, _, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    eager, piped = cuda_model(spec, params), cuda_model(spec, params)
+    piped.cuda_graph = True
+    piped.pipeline_geometry = True
+    keys = [k for k, _ in eager.named_parameters()]
+    batches = []
+    for step in range(8):
+        data, _, domain = synthetic.make_batch(spec['layout'], seed=300 + step, **TINY_SHAPE)
+        batches.append(FoamData(data, labels, domain).to('cuda'))
+    announce = {0: 1, 1: 2, 2: 3, 3: None, 4: 7, 5: 6, 6: 7}      # step -> announced next (None: no hint, 4: a wrong one)
+    for step, batch in enumerate(batches):
+        for m in (eager, piped):
+            for p in m.parameters():
+                p.grad = None
+        l0 = eager.training_step(batch, step)
+        l0.backward()
+        nxt = announce.get(step)
+        if nxt is not None:
+            piped.announce_next_batch(batches[nxt])
+        l1 = piped.training_step(batch, step)
+        l1.backward()
+        assert abs(float(l0) - float(l1)) <= 1e-6 * abs(float(l0)), step
+        g0 = {k: p.grad for k, p in eager.named_parameters()}
+        g1 = {k: p.grad for k, p in piped.named_parameters()}
+        assert rel_l2(flat(g1, keys), flat(g0, keys)) < 1e-6, step
+    assert len(piped.executor._graphs) == 1 and next(iter(piped.executor._graphs.values())).pipeline
