@@ -289,9 +289,8 @@ def main():
     geo = None
 
     def load_static(src: FoamData, dst: FoamData = static):
-        dst.data.copy_(src.data, non_blocking=True)
-        for k, v in src.domain.items():
-            dst.domain[k].copy_(v, non_blocking=True)
+        names = list(src.domain)      # the batch tensor and every sub-domain's ids in one launch
+        ops.copy_blocks_multi([src.data] + [src.domain[k] for k in names], [dst.data] + [dst.domain[k] for k in names])
 
     def eager_step(batch):
         return trainer.train_step(batch, args.laplacian)

@@ -428,17 +428,26 @@ def gather_blocks(src: Tensor, ids: Tensor) -> Tensor:
     return out
 
 
-def gather_blocks_multi(srcs, ids: Tensor) -> list:
-    """[src[ids] for src in srcs] along dimension 0 in one launch (at most 16 tensors; empty blocks allowed)."""
+def gather_blocks_multi(srcs, ids: Tensor, outs: Optional[list] = None) -> list:
+    """[src[ids] for src in srcs] along dimension 0 in one launch (at most 16 tensors; empty blocks allowed).
+    `outs`: preallocated destinations (static buffers of a captured graph)."""
     lib = _lib.load()
     if ids.dtype != torch.int64 or not ids.is_cuda:
         raise _lib.PcfdError('gather_blocks_multi: ids must be a CUDA int64 tensor')
     ids = ids.contiguous()
-    outs, nbytes = [], []
-    for src in srcs:
+    given = outs is not None
+    outs = list(outs) if given else []
+    nbytes = []
+    for i, src in enumerate(srcs):
         if not src.is_cuda or not src.is_contiguous():
             raise _lib.PcfdError('gather_blocks_multi: sources must be contiguous CUDA tensors')
-        outs.append(torch.empty((ids.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device))
+        shape = (ids.numel(),) + tuple(src.shape[1:])
+        if given:
+            o = outs[i]
+            if tuple(o.shape) != shape or o.dtype != src.dtype or not o.is_contiguous() or not o.is_cuda:
+                raise _lib.PcfdError('gather_blocks_multi: destination does not match its source')
+        else:
+            outs.append(torch.empty(shape, dtype=src.dtype, device=src.device))
         nbytes.append(src[0].numel() * src.element_size() if src.shape[0] else 0)
     n = len(srcs)
     src_arr = (C.c_void_p * n)(*[s.data_ptr() for s in srcs])
@@ -449,6 +458,20 @@ def gather_blocks_multi(srcs, ids: Tensor) -> list:
       check(lib.pcfd_gather_blocks_multi(src_arr, dst_arr, len_arr, n, ids.data_ptr(), ids.numel(), _stream()),
             'pcfd_gather_blocks_multi')
     return outs
+
+
+_IDENTITY_IDS: dict = {}
+
+
+def copy_blocks_multi(srcs, dsts) -> None:
+    """dst[i] <- src[i] for up to 16 equally batched tensors in ONE launch (a batch into the static input buffers of
+    a captured step: the data tensor and every sub-domain's ids) instead of one copy kernel per tensor."""
+    b = srcs[0].shape[0]
+    key = (b, srcs[0].device)
+    ids = _IDENTITY_IDS.get(key)
+    if ids is None:
+        ids = _IDENTITY_IDS[key] = torch.arange(b, dtype=torch.int64, device=srcs[0].device)
+    gather_blocks_multi(srcs, ids, outs=dsts)
 
 
 def set_gemm_engine(engine: int) -> None:
