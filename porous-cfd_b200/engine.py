@@ -270,7 +270,7 @@ class GraphedStep:
         self.pipeline = pipeline and ex.uses_geometry()
         self.load(data, domain)
         self.geo = None
-        self.expected = None          # signature of the batch whose geometry the static buffers hold
+        self.expected = None          # (data, version, boundary ids, version) of the batch whose geometry the static buffers hold
         if self.pipeline:
             # the only input of the geometry branch: the next batch's sampled positions, gathered into a static buffer
             self.pos_next = ex.geometry_positions(self.data, labels, self.domain)
@@ -292,9 +292,12 @@ class GraphedStep:
             else:
                 self.result = ex.step(self.data, labels, self.domain, laplacian)
 
-    @staticmethod
-    def _sig(data: Tensor):
-        return (data.data_ptr(), data._version, tuple(data.shape))
+    def _announced(self, data: Tensor, domain: dict) -> bool:
+        """Are these the tensors the previous call announced, unmodified since?  The announced tensors are kept
+        referenced, so their memory cannot have been handed to another batch in between."""
+        e = self.expected
+        ids = domain['boundary']
+        return e is not None and e[0] is data and e[1] == data._version and e[2] is ids and e[3] == ids._version
 
     def load(self, data: Tensor, domain: dict) -> None:
         names = list(self.domain)
@@ -310,7 +313,7 @@ class GraphedStep:
     def run(self, data: Tensor, domain: dict, next_data: Optional[Tensor] = None, next_domain: Optional[dict] = None) -> 'StepResult':
         self.load(data, domain)
         if self.pipeline:
-            if self.expected != self._sig(data):
+            if not self._announced(data, domain):
                 # not announced by the previous call: geometry of this batch in line, into the static buffers
                 fresh = self.ex.geometry(self.data, self.labels, self.domain)
                 for cur, new in zip(self.geo, fresh):
@@ -319,7 +322,7 @@ class GraphedStep:
             if next_data is None:
                 next_data, next_domain = data, domain
             self.ex.geometry_positions(next_data, self.labels, next_domain, out=self.pos_next)     # one launch
-            self.expected = self._sig(next_data)
+            self.expected = (next_data, next_data._version, next_domain['boundary'], next_domain['boundary']._version)
         self.graph.replay()
         return self.result
 
