@@ -222,6 +222,7 @@ def main():
                     help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 1 = tcgen05 with thread-staged operands, 0 = fp32 FFMA')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sync-loss', action='store_true', help='end-to-end leg: blocking float(loss) every step instead of the delayed read')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='compute the set-abstraction geometry (FPS, ball query) of a batch inside its own step instead of one step ahead')
     ap.add_argument('--laplacian', default='reference', choices=['reference', 'true'])
@@ -416,7 +417,24 @@ def main():
         if world > 1:
             dist.all_reduce(flat)                 # one NCCL all-reduce; 1/world is folded into the Adam kernel
         trainer.step(flat)                        # fused Adam on the flat parameter buffer (one launch)
-        return float(loss.detach())               # device -> host read of the step's result
+        if args.sync_loss:
+            return float(loss.detach())           # blocking device -> host read of the step's result
+        # device -> host read of EVERY step's loss through a pinned buffer; the host looks at it one step later (what a
+        # logging callback does), so the GPU already has the next step queued while the host waits for this one
+        slot = i & 1
+        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ev[slot] = torch.cuda.Event()
+        loss_ev[slot].record()
+        return read_loss(slot ^ 1)
+
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [None, None]
+
+    def read_loss(slot):
+        if loss_ev[slot] is None:
+            return None
+        loss_ev[slot].synchronize()
+        return float(loss_host[slot])
 
     for i in range(W):
         e2e_step(i)
@@ -425,6 +443,8 @@ def main():
     f0.record()
     for i in range(K):
         e2e_step(W + i)
+    if not args.sync_loss:
+        read_loss((W + K - 1) & 1)                # the last step's loss is read inside the timed region too
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -521,8 +541,10 @@ def main():
                        'l2': 'per-step working set (jets + gradients ~1 GB) exceeds the 126 MB L2; 4 batches cycled, no flush'},
             'loss': loss_value, 'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'ms_per_step': ms_e2e / K, 'h2d_bytes_per_step': h2d_bytes,
-                    'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); '
-                           'FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]'},
+                    'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); ' +
+                           ('FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]' if args.sync_loss else
+                            'FlatAdamTrainer.step(); loss copied to pinned host memory every step and read by the host one step later  '
+                            '[next batches prefetched on a copy stream]')},
             'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu, 'ingest': ingest}
     _emit(line)
     if world > 1:
