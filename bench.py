@@ -521,7 +521,11 @@ def main():
 
     ingest = None
     if world == 1:
-        ingest = ingest_leg(dev_batches, labels, SHAPE['n_internal'], spec['dims'], peaks)
+        try:
+            ingest = ingest_leg(dev_batches, labels, SHAPE['n_internal'], spec['dims'], peaks)
+        except Exception as e:      # an auxiliary measurement must not cost the bench line
+            ingest = {'error': f'{type(e).__name__}: {e}'}
+            torch.cuda.synchronize()
 
     cpu = None
     if not args.no_cpu_baseline:
