@@ -126,11 +126,48 @@ int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_plane_stride, int32
 int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots,
                     int64_t n_seg, int32_t seg_len, int32_t c,
                     float* out, int32_t ldout, int32_t* arg, void* stream);
+/* The same, also writing zsel[s][c] = z[s*seg_len + arg[s][c]][c], the PRE-activation of the selected row (0 for an
+ * empty segment): what the sparse backward below needs for act'(.) without a second, dependent gather. */
+int pcfd_segmax_fwd_z(const float* z, int32_t ldz, int32_t act, const int32_t* slots,
+                      int64_t n_seg, int32_t seg_len, int32_t c,
+                      float* out, int32_t ldout, int32_t* arg, float* zsel, int32_t ldzsel, void* stream);
 /* gz[s*seg_len + j][c] = (j == arg[s][c]) ? gout[s][c] * act'(z) : 0   (gz fully overwritten) */
 int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t* arg,
                     const float* z, int32_t ldz, int32_t act,
                     int64_t n_seg, int32_t seg_len, int32_t c,
                     float* gz, int32_t ldgz, void* stream);
+
+/*
+ * Backward of "last layer of a value-only MLP -> max pool" in sparse form.  Every pooled encoder of the reference
+ * ends in  out[s][c] = max_j act(z[s*seg_len + j][c]),  z = T(zin) W^T + b  (PointNetConv max aggregation
+ * models/modules.py:286-292, GlobalSetAbstraction :412-423, Branch :184-190, GeometryEncoder :206-214), so the
+ * cotangent of z has one non-zero entry per (segment, channel), at row arg[s][c].  Instead of materialising it
+ * (pcfd_segmax_bwd) and running the dense dX / dW over all rows, this entry point ACCUMULATES
+ *     gw[c][:] += g[s][c] * T(zin)[s*seg_len + arg[s][c]][:],   gbias[c] += g[s][c]        (gw / gbias optional)
+ * and OVERWRITES (optional)
+ *     gzin[s*seg_len + j][:] = T'(zin) * sum_{c: arg[s][c] == j} g[s][c] * W[c][:]          (zero rows where nothing pooled)
+ * with g[s][c] = gout[s][c] * act'(zsel[s][c]) (zsel from pcfd_segmax_fwd_z).  Fixed summation order (deterministic).
+ * `tin_host` may carry an activation over all k columns; dropout / escale / partial activation are not supported
+ * here (pcfd_pool_layer_bwd_supported returns 0 and the caller takes pcfd_segmax_bwd + the dense layer backward).
+ */
+int pcfd_pool_layer_bwd_supported(int64_t n_seg, int32_t seg_len, int32_t k, int32_t c, const pcfd_intrans_t* tin_host,
+                                  int32_t ldzin);
+size_t pcfd_pool_layer_bwd_workspace_bytes(int64_t n_seg, int32_t seg_len, int32_t k, int32_t c);
+int pcfd_pool_layer_bwd(const float* gout, int32_t ldgout, const int32_t* arg, const float* zsel, int32_t ldzsel,
+                        int32_t act_pool, int64_t n_seg, int32_t seg_len, int32_t c,
+                        const float* zin, int32_t ldzin, const pcfd_intrans_t* tin_host, int32_t k,
+                        const float* w, int32_t ldw, float* gw, int32_t ldgw, float* gbias,
+                        float* gzin, int32_t ldgzin, void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * Long segments (seg_len > c, global pools over thousands of points): at most c rows of a segment receive gradient,
+ * and every layer in front of the pool acts row by row, so their backward may run on those rows alone.  Emits the
+ * compacted problem: ids[s][ch] = arg[s][ch] (int64 row inside the segment, 0 for an empty segment) and the cotangent
+ * gzc[(s*c + ch)][:] = g[s][ch] * e_ch of compact row (s, ch) (all ldgzc columns written).  A row selected by several
+ * channels appears once per channel: the backward is linear in the cotangent, so the contributions add up.
+ */
+int pcfd_pool_compact(const float* gout, int32_t ldgout, const int32_t* arg, const float* zsel, int32_t ldzsel,
+                      int32_t act_pool, int64_t n_seg, int32_t c,
+                      int64_t* ids, float* gzc, int32_t ldgzc, void* stream);
 
 /*
  * Farthest point sampling, one CTA per geometry; torch_cluster.fps(pos, batch, ratio) as called at

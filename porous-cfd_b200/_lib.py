@@ -58,7 +58,13 @@ SIGNATURES = {
     'pcfd_jet_linear_bwd_dw': (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _IT, _P, _I32, _P, _P, _I32,
                                          _I32, _I64, _I64, _I32, _I32, _P, _SZ, _P]),
     'pcfd_segmax_fwd': (C.c_int, [_P, _I32, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P]),
+    'pcfd_segmax_fwd_z': (C.c_int, [_P, _I32, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P]),
     'pcfd_segmax_bwd': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _I64, _I32, _I32, _P, _I32, _P]),
+    'pcfd_pool_layer_bwd_supported': (C.c_int, [_I64, _I32, _I32, _I32, _IT, _I32]),
+    'pcfd_pool_layer_bwd_workspace_bytes': (_SZ, [_I64, _I32, _I32, _I32]),
+    'pcfd_pool_layer_bwd': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _I64, _I32, _I32, _P, _I32, _IT, _I32, _P, _I32, _P, _I32,
+                                      _P, _P, _I32, _P, _SZ, _P]),
+    'pcfd_pool_compact': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _P, _I32, _P]),
     'pcfd_fps': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     'pcfd_fps_workspace_bytes': (C.c_size_t, [_I32, _I32, _I32]),
     'pcfd_fps_ws': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, C.c_size_t, _P]),

@@ -8,36 +8,40 @@ namespace pcfd {
 __global__ void __launch_bounds__(256) segmax_fwd_kernel(const float* __restrict__ z, int ldz, int act,
                                                          const int32_t* __restrict__ slots, int64_t n_seg,
                                                          int seg_len, int c, float* __restrict__ out, int ldout,
-                                                         int32_t* __restrict__ arg) {
+                                                         int32_t* __restrict__ arg, float* __restrict__ zsel, int ldzsel) {
   __shared__ float sv[8][33];
+  __shared__ float sz[8][33];
   __shared__ int si[8][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
   const int col = blockIdx.y * 32 + lane;
   const int64_t seg = blockIdx.x;
-  float best = -INFINITY;
+  float best = -INFINITY, bestz = 0.0f;
   int besti = -1;
   if (col < c) {
     const float* base = z + seg * (int64_t)seg_len * ldz + col;
     for (int j = wy; j < seg_len; j += 8) {
       if (slots != nullptr && __ldg(slots + seg * seg_len + j) < 0) continue;
-      const float v = act_value(act, __ldg(base + (int64_t)j * ldz));
-      if (v > best || besti < 0) { best = v; besti = j; }   // strictly greater: first maximum wins inside a lane
+      const float zz = __ldg(base + (int64_t)j * ldz);
+      const float v = act_value(act, zz);
+      if (v > best || besti < 0) { best = v; besti = j; bestz = zz; }   // strictly greater: first maximum wins inside a lane
     }
   }
   sv[wy][lane] = best;
+  sz[wy][lane] = bestz;
   si[wy][lane] = besti;
   __syncthreads();
   if (wy == 0 && col < c) {
-    float b = sv[0][lane];
+    float b = sv[0][lane], bz = sz[0][lane];
     int bi = si[0][lane];
 #pragma unroll
     for (int i = 1; i < 8; ++i) {
       const float v = sv[i][lane];
       const int vi = si[i][lane];
-      if (vi >= 0 && (bi < 0 || v > b || (v == b && vi < bi))) { b = v; bi = vi; }
+      if (vi >= 0 && (bi < 0 || v > b || (v == b && vi < bi))) { b = v; bi = vi; bz = sz[i][lane]; }
     }
     out[seg * ldout + col] = bi >= 0 ? b : 0.0f;
     arg[seg * c + col] = bi;
+    if (zsel != nullptr) zsel[seg * ldzsel + col] = bi >= 0 ? bz : 0.0f;
   }
 }
 
@@ -65,13 +69,15 @@ __global__ void __launch_bounds__(256) segmax_bwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) segmax_short_fwd_kernel(const float* __restrict__ z, int ldz, int act,
                                                                const int32_t* __restrict__ slots, int64_t n_seg,
                                                                int seg_len, int c, float* __restrict__ out, int ldout,
-                                                               int32_t* __restrict__ arg) {
+                                                               int32_t* __restrict__ arg, float* __restrict__ zsel,
+                                                               int ldzsel) {
   const int lane = threadIdx.x & 31;
   const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (seg >= n_seg) return;
   const int col = blockIdx.y * 128 + lane * 4;
   const bool active = col < c;            // no early exit: the whole warp takes part in the ballots below
   float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float bz[4] = {0.f, 0.f, 0.f, 0.f};
   int bi[4] = {-1, -1, -1, -1};
   const float* base = z + seg * (int64_t)seg_len * ldz + col;
   // slot validity of up to 96 slots as three ballot words (lane j looks at slots j, j+32, j+64), so that the row loop
@@ -99,10 +105,11 @@ __global__ void __launch_bounds__(256) segmax_short_fwd_kernel(const float* __re
     for (int u = 0; u < 4; ++u) {
       if (!ok[u]) continue;
       const int j = j0 + u;
+      const float zz[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
       const float v[4] = {act_value(act, x[u].x), act_value(act, x[u].y), act_value(act, x[u].z), act_value(act, x[u].w)};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (v[e] > best[e] || bi[e] < 0) { best[e] = v[e]; bi[e] = j; }
+        if (v[e] > best[e] || bi[e] < 0) { best[e] = v[e]; bi[e] = j; bz[e] = zz[e]; }
     }
   }
 #pragma unroll
@@ -110,6 +117,7 @@ __global__ void __launch_bounds__(256) segmax_short_fwd_kernel(const float* __re
     if (active && col + e < c) {
       out[seg * ldout + col + e] = bi[e] >= 0 ? best[e] : 0.0f;
       arg[seg * c + col + e] = bi[e];
+      if (zsel != nullptr) zsel[seg * ldzsel + col + e] = bi[e] >= 0 ? bz[e] : 0.0f;
     }
   }
 }
@@ -143,19 +151,26 @@ __global__ void __launch_bounds__(256) segmax_short_bwd_kernel(const float* __re
 
 using namespace pcfd;
 
-extern "C" int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots, int64_t n_seg,
-                               int32_t seg_len, int32_t c, float* out, int32_t ldout, int32_t* arg, void* stream) {
-  if (!z || !out || !arg || n_seg <= 0 || seg_len <= 0 || c <= 0) return PCFD_ERR_ARG;
+extern "C" int pcfd_segmax_fwd_z(const float* z, int32_t ldz, int32_t act, const int32_t* slots, int64_t n_seg,
+                                 int32_t seg_len, int32_t c, float* out, int32_t ldout, int32_t* arg, float* zsel,
+                                 int32_t ldzsel, void* stream) {
+  if (!z || !out || !arg || n_seg <= 0 || seg_len <= 0 || c <= 0 || (zsel && ldzsel < c)) return PCFD_ERR_ARG;
   if (seg_len <= 96 && ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0) {
     dim3 sgrid((unsigned)((n_seg + 7) / 8), (unsigned)((c + 127) / 128));
-    segmax_short_fwd_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg);
+    segmax_short_fwd_kernel<<<sgrid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg,
+                                                                     zsel, ldzsel);
     PCFD_CHECK_LAUNCH();
     return PCFD_OK;
   }
   dim3 grid((unsigned)n_seg, (unsigned)((c + 31) / 32));
-  segmax_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg);
+  segmax_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg, zsel, ldzsel);
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
+}
+
+extern "C" int pcfd_segmax_fwd(const float* z, int32_t ldz, int32_t act, const int32_t* slots, int64_t n_seg,
+                               int32_t seg_len, int32_t c, float* out, int32_t ldout, int32_t* arg, void* stream) {
+  return pcfd_segmax_fwd_z(z, ldz, act, slots, n_seg, seg_len, c, out, ldout, arg, nullptr, 0, stream);
 }
 
 extern "C" int pcfd_segmax_bwd(const float* gout, int32_t ldgout, const int32_t* arg, const float* z, int32_t ldz,

@@ -133,6 +133,63 @@ def chain_backward(ctx: StepContext, layers, zs, gz: Jet, rows_per_geom: int, es
     return gz if need_input_grad else None
 
 
+def pool_backward(ctx: StepContext, layers, zs, gout: Tensor, ldgout: int, arg: Tensor, zsel: Tensor, act_pool, n_seg: int,
+                  seg_len: int,
+                  rows_per_geom: int = 0, need_input_grad: bool = False,
+                  side: Optional[torch.cuda.Stream] = None) -> Optional[Jet]:
+    """Reverse pass of `chain(layers) -> max pool over segments of seg_len rows`.  The cotangent of the last layer's
+    output has one non-zero entry per (segment, channel), so instead of materialising it (segmax_bwd) and running the
+    dense dX / dW over every row:
+      * short / medium segments (set-abstraction neighbourhoods, global set abstraction): sparse last-layer backward
+        (ops.pool_layer_bwd), then the ordinary dense reverse pass of the layers in front of it;
+      * long segments with fewer channels than rows (PI-GANO geometry / branch encoders): only the <= C selected rows of a
+        segment carry gradient and every layer acts row by row, so the whole reverse pass runs on the compacted rows;
+      * anything else (dropout / branch scaling on the last layer): the dense form.
+    Measured on B200 (scripts/bench_pool.py): the sparse kernels are CUDA-core kernels with ~10 instructions per gathered
+    16-byte chunk, the dense form runs on the tensor cores; with K + 1 = 17 slots per neighbourhood (config 2) the dense
+    form is as fast (174 vs 183 us for 272 000 edge rows 64 -> 128), from ~48 slots on (windbreaks: 65) and for thin inputs
+    (k <= 16, manufactured set abstraction) the sparse form wins (207 vs 290 us; 34 vs 226 us), so that is the switch.
+    PCFD_POOL_SPARSE=0 forces the dense form, =2 the sparse form wherever it is supported (tests compare them)."""
+    L = layers[-1]
+    zlast, zin = zs[-1], zs[-2]
+    c, k = L.n, L.k
+    tin = _tin(ctx, L, None, 0)
+    plain = L.cvec_key is None and not L.escale and L.col_lo == 0 and (not ctx.training or L.drop_p == 0.0)
+    mode = os.environ.get('PCFD_POOL_SPARSE', '1')
+    worth = mode == '2' or k <= 16 or (seg_len >= 48 and n_seg >= 512)
+    if mode != '0' and worth and plain and ops.pool_layer_bwd_supported(n_seg, seg_len, k, c, tin, zin.ld):
+        need_gzin = len(layers) > 1 or need_input_grad
+        ctx.need_workspace(ops.pool_layer_bwd_workspace_bytes(n_seg, seg_len, k, c))
+        main = torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(main)
+            gout.record_stream(side)
+            with torch.cuda.stream(side):
+                ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
+                                   ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.workspace)
+        else:
+            ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
+                               ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.workspace)
+        if not need_gzin:
+            return None
+        gzin = ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
+                                  None, None, True, None)
+        if len(layers) == 1:
+            return gzin
+        return chain_backward(ctx, layers[:-1], zs[:-1], gzin, rows_per_geom, need_input_grad=need_input_grad, side=side)
+    no_drop = all((not ctx.training or l.drop_p == 0.0) and not l.escale and l.cvec_key is None for l in layers)
+    if mode != '0' and seg_len > c and not need_input_grad and no_drop:
+        ids, gzc = ops.pool_compact(gout, ldgout, arg, zsel, act_pool, n_seg, c)
+        zs_c = []
+        for zj in zs[:-1]:
+            zc = Jet.empty(1, n_seg * c, zj.width, zj.t.device)
+            ops.gather_cols(zj.t, n_seg, seg_len, zj.ld, ids, 0, c, list(range(zj.width)), zc.t, zc.ld, c)
+            zs_c.append(zc)
+        return chain_backward(ctx, layers, zs_c, gzc, 0, need_input_grad=False, side=side)
+    gz = ops.segmax_bwd(gout, ldgout, arg, zlast.t[0], act_pool, n_seg, seg_len, c)
+    return chain_backward(ctx, layers, zs, Jet(gz, c), rows_per_geom, need_input_grad=need_input_grad, side=side)
+
+
 # ------------------------------------------------------------------------------------------------
 # set-abstraction stack (models/modules.py:94-98, 295-325, 403-423, 483-527)
 # ------------------------------------------------------------------------------------------------
@@ -186,8 +243,8 @@ def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int,
         ein = ops.sa_gather(x, ldx, f, pos, idx, slots, lvl.radius)
         zs = chain_forward(ctx, lvl.layers, Jet(ein, f + d), 0)
         c = lvl.layers[-1].n
-        out, arg = ops.segmax_fwd(zs[-1].t[0], lvl.act, slots, b * m, slots.shape[1], c)
-        saved['levels'].append({'slots': slots, 'zs': zs, 'arg': arg, 'm': m, 'n': n, 'f_in': f, 'ldx': ldx, 'c': c})
+        out, arg, zsel = ops.segmax_fwd_z(zs[-1].t[0], lvl.act, slots, b * m, slots.shape[1], c)
+        saved['levels'].append({'slots': slots, 'zs': zs, 'arg': arg, 'zsel': zsel, 'm': m, 'n': n, 'f_in': f, 'ldx': ldx, 'c': c})
         x, ldx, f, pos, n = out, out.stride(0), c, newpos, m
     if stack.global_layers is None:
         raise NotImplementedError('a set-abstraction stack without a final GlobalSetAbstraction is not used by any '
@@ -197,17 +254,17 @@ def sa_forward(ctx: StepContext, stack: SAStack, x0: Tensor, ldx0: int, f0: int,
     ops.gather_cols(pos, 1, b * n, d, None, 0, b * n, list(range(d)), gin, gin.stride(1), b * n, 0, f)
     zs = chain_forward(ctx, stack.global_layers, Jet(gin, f + d), n)
     e = stack.global_layers[-1].n
-    g, arg = ops.segmax_fwd(zs[-1].t[0], stack.act, None, b, n, e)
-    saved.update({'g_zs': zs, 'g_arg': arg, 'g_n': n, 'g_f': f, 'e': e})
+    g, arg, zsel = ops.segmax_fwd_z(zs[-1].t[0], stack.act, None, b, n, e)
+    saved.update({'g_zs': zs, 'g_arg': arg, 'g_zsel': zsel, 'g_n': n, 'g_f': f, 'e': e})
     return g, saved
 
 
 def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg: int, side=None) -> None:
     b, n, e = saved['b'], saved['g_n'], saved['e']
     zs = saved['g_zs']
-    gz = ops.segmax_bwd(gg, ldgg, saved['g_arg'], zs[-1].t[0], stack.act, b, n, e)
     need = len(stack.levels) > 0
-    gin = chain_backward(ctx, stack.global_layers, zs, Jet(gz, e), n, need_input_grad=need, side=side)
+    gin = pool_backward(ctx, stack.global_layers, zs, gg, ldgg, saved['g_arg'], saved['g_zsel'], stack.act, b, n, rows_per_geom=n,
+                        need_input_grad=need, side=side)
     if not need:
         return
     gx, ldgx = gin.t[0], gin.ld
@@ -215,8 +272,8 @@ def sa_backward(ctx: StepContext, stack: SAStack, saved: dict, gg: Tensor, ldgg:
         lvl, sv = stack.levels[li], saved['levels'][li]
         m_total = sv['slots'].shape[0]
         zs = sv['zs']
-        gz = ops.segmax_bwd(gx, ldgx, sv['arg'], zs[-1].t[0], lvl.act, m_total, sv['slots'].shape[1], sv['c'])
-        gein = chain_backward(ctx, lvl.layers, zs, Jet(gz, sv['c']), 0, need_input_grad=(li > 0), side=side)
+        gein = pool_backward(ctx, lvl.layers, zs, gx, ldgx, sv['arg'], sv['zsel'], lvl.act, m_total, sv['slots'].shape[1],
+                             need_input_grad=(li > 0), side=side)
         if li > 0:
             gprev = torch.empty((b * sv['n'], sv['ldx']), dtype=torch.float32, device=gx.device)
             ops.zero_(gprev)
@@ -377,13 +434,12 @@ class PinnExecutor:
     def _segmax_features(self, ctx, layers, pending_act, zin: Jet, n_seg: int, seg_len: int):
         zs = chain_forward(ctx, layers, zin, seg_len)
         c = layers[-1].n
-        out, arg = ops.segmax_fwd(zs[-1].t[0], pending_act, None, n_seg, seg_len, c)
-        return out, {'zs': zs, 'arg': arg, 'n_seg': n_seg, 'seg_len': seg_len, 'c': c, 'act': pending_act}
+        out, arg, zsel = ops.segmax_fwd_z(zs[-1].t[0], pending_act, None, n_seg, seg_len, c)
+        return out, {'zs': zs, 'arg': arg, 'zsel': zsel, 'n_seg': n_seg, 'seg_len': seg_len, 'c': c, 'act': pending_act}
 
     def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False):
-        gz = ops.segmax_bwd(gout, ldgout, sv['arg'], sv['zs'][-1].t[0], sv['act'], sv['n_seg'], sv['seg_len'], sv['c'])
-        return chain_backward(ctx, layers, sv['zs'], Jet(gz, sv['c']), sv['seg_len'], need_input_grad=need_input_grad,
-                              side=ctx.side_stream if ctx.overlap else None)
+        return pool_backward(ctx, layers, sv['zs'], gout, ldgout, sv['arg'], sv['zsel'], sv['act'], sv['n_seg'], sv['seg_len'],
+                             rows_per_geom=sv['seg_len'], need_input_grad=need_input_grad, side=ctx.side_stream if ctx.overlap else None)
 
     # ---- encode: per-geometry constants ------------------------------------------------------
     def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor],

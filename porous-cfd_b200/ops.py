@@ -212,6 +212,20 @@ def segmax_fwd(z: Tensor, act, slots: Optional[Tensor], n_seg: int, seg_len: int
     return out, arg
 
 
+def segmax_fwd_z(z: Tensor, act, slots: Optional[Tensor], n_seg: int, seg_len: int, c: int):
+    """segmax_fwd that also returns zsel [n_seg, c]: the pre-activation of each selected row (for pool_layer_bwd)."""
+    lib = _lib.load()
+    out = torch.empty((n_seg, round4(c)), dtype=torch.float32, device=z.device)
+    arg = torch.empty((n_seg, c), dtype=torch.int32, device=z.device)
+    zsel = torch.empty((n_seg, c), dtype=torch.float32, device=z.device)
+    _lib.launches += 1
+    with _timed('segmax_fwd', 4.0 * n_seg * seg_len * c):
+      check(lib.pcfd_segmax_fwd_z(z.data_ptr(), z.stride(0), ACT_CODES[act], _ptr(slots), n_seg, seg_len, c,
+                                  out.data_ptr(), out.stride(0), arg.data_ptr(), zsel.data_ptr(), zsel.stride(0), _stream()),
+            'pcfd_segmax_fwd_z')
+    return out, arg, zsel
+
+
 def segmax_bwd(gout: Tensor, ldgout: int, arg: Tensor, z: Tensor, act, n_seg: int, seg_len: int, c: int) -> Tensor:
     lib = _lib.load()
     gz = torch.empty((1, n_seg * seg_len, z.stride(0)), dtype=torch.float32, device=z.device)
@@ -220,6 +234,48 @@ def segmax_bwd(gout: Tensor, ldgout: int, arg: Tensor, z: Tensor, act, n_seg: in
       check(lib.pcfd_segmax_bwd(gout.data_ptr(), ldgout, arg.data_ptr(), z.data_ptr(), z.stride(0), ACT_CODES[act],
                               n_seg, seg_len, c, gz.data_ptr(), gz.stride(1), _stream()), 'pcfd_segmax_bwd')
     return gz
+
+
+def pool_layer_bwd_supported(n_seg: int, seg_len: int, k: int, c: int, tin: Optional[InTrans], ldzin: int) -> bool:
+    return bool(_lib.load().pcfd_pool_layer_bwd_supported(n_seg, seg_len, k, c, C.byref(tin) if tin is not None else None,
+                                                          ldzin))
+
+
+def pool_layer_bwd_workspace_bytes(n_seg: int, seg_len: int, k: int, c: int) -> int:
+    return int(_lib.load().pcfd_pool_layer_bwd_workspace_bytes(n_seg, seg_len, k, c))
+
+
+def pool_layer_bwd(gout: Tensor, ldgout: int, arg: Tensor, zsel: Tensor, act_pool, n_seg: int, seg_len: int, c: int,
+                   zin: Jet, tin: Optional[InTrans], k: int, w: Tensor, gw: Optional[Tensor], gbias: Optional[Tensor],
+                   need_gzin: bool, workspace: Optional[Tensor]) -> Optional[Jet]:
+    """Sparse backward of (last MLP layer -> max pool): accumulates gw / gbias, returns the gradient of the layer's
+    input pre-activations (Jet, cj = 1) when `need_gzin`.  zsel [n_seg, c] = the layer's output at the selected rows
+    (segmax_fwd_z), zin its inputs; w is the [c][k] weight (row stride w.stride(0))."""
+    lib = _lib.load()
+    gzin = Jet.empty(1, zin.rows, k, zin.t.device) if need_gzin else None
+    want_w = gw is not None or gbias is not None
+    _lib.launches += (2 if want_w else 0) + (1 if need_gzin else 0)
+    with _timed('pool_layer_bwd', 2.0 * n_seg * c * k * ((1 if want_w else 0) + (1 if need_gzin else 0)),
+                4.0 * n_seg * seg_len * k * ((1 if want_w else 0) + (2 if need_gzin else 0)) + 16.0 * n_seg * c):
+      check(lib.pcfd_pool_layer_bwd(gout.data_ptr(), ldgout, arg.data_ptr(), zsel.data_ptr(), zsel.stride(0), ACT_CODES[act_pool],
+                                    n_seg, seg_len, c, zin.t.data_ptr(), zin.ld, C.byref(tin) if tin is not None else None,
+                                    k, w.data_ptr(), w.stride(0), _ptr(gw), gw.stride(0) if gw is not None else 0,
+                                    _ptr(gbias), gzin.t.data_ptr() if gzin is not None else None,
+                                    gzin.ld if gzin is not None else 0, _ptr(workspace),
+                                    workspace.numel() * workspace.element_size() if workspace is not None else 0,
+                                    _stream()), 'pcfd_pool_layer_bwd')
+    return gzin
+
+
+def pool_compact(gout: Tensor, ldgout: int, arg: Tensor, zsel: Tensor, act_pool, n_seg: int, c: int):
+    """-> (ids int64 [n_seg, c] rows inside each segment, gzc Jet [1, n_seg*c, ld] cotangent of the compacted rows)."""
+    lib = _lib.load()
+    ids = torch.empty((n_seg, c), dtype=torch.int64, device=zsel.device)
+    gzc = Jet.empty(1, n_seg * c, c, zsel.device)
+    _lib.launches += 1
+    check(lib.pcfd_pool_compact(gout.data_ptr(), ldgout, arg.data_ptr(), zsel.data_ptr(), zsel.stride(0), ACT_CODES[act_pool],
+                                n_seg, c, ids.data_ptr(), gzc.t.data_ptr(), gzc.ld, _stream()), 'pcfd_pool_compact')
+    return ids, gzc
 
 
 def fps(pos: Tensor, ratio: float) -> Tensor:

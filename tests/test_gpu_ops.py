@@ -373,3 +373,112 @@ def test_fused_adam_matches_torch(ops):
         opt.param_groups[0]['lr'] *= 0.999
         lr.mul_(0.999)
     assert int(step.item()) == 4
+
+
+# ---------------------------------------------------------------------------------------------
+# sparse backward of (last MLP layer -> max pool) and the compacted backward of long segments
+# ---------------------------------------------------------------------------------------------
+
+POOL_CASES = [  # n_seg, seg_len, k, c, act_in, act_pool, masked slots
+    (500, 17, 64, 128, 'silu', 'silu', True),       # set abstraction level 0 of config 2 (K + 1 = 17 slots)
+    (130, 17, 128, 256, 'silu', 'silu', True),      # level 1
+    (8, 125, 256, 1024, 'silu', 'silu', False),     # global set abstraction: medium segments, many channels
+    (40, 65, 131, 128, None, 'silu', True),         # single-layer level (windbreaks SA1): raw edge features, odd k
+    (64, 9, 6, 64, None, 'tanh', False),            # manufactured SA0 [6, 64]
+    (3, 300, 40, 50, 'tanh', 'tanh', False),        # more rows than channels
+]
+
+
+@pytest.mark.parametrize('case', POOL_CASES)
+def test_pool_layer_bwd_matches_autograd(ops, case):
+    n_seg, L, k, c, act_in, act_pool, masked = case
+    from porous_cfd_b200.ops import Jet
+    g = torch.Generator().manual_seed(n_seg + L + k)
+    rows = n_seg * L
+    zin = torch.randn(rows, k, generator=g)
+    w = torch.randn(c, k, generator=g) / math.sqrt(k)
+    b = torch.randn(c, generator=g)
+    gout = torch.randn(n_seg, c, generator=g)
+    slots = None
+    if masked:
+        slots = torch.where(torch.rand(n_seg, L, generator=g) < 0.3, -1, 1).int()
+        slots[:, 0] = 1                                   # a segment always keeps its self loop
+    fa = {None: lambda x: x, 'silu': torch.nn.functional.silu, 'tanh': torch.tanh}
+    zr = zin.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    br = b.double().requires_grad_(True)
+    zo = fa[act_in](zr) @ wr.t() + br
+    vals = fa[act_pool](zo).reshape(n_seg, L, c)
+    if masked:
+        vals = vals.masked_fill((slots < 0)[:, :, None], -float('inf'))
+    ref_arg = vals.max(dim=1).indices
+
+    zj = Jet.empty(1, rows, k, 'cuda'); zj.t[0, :, :k].copy_(zin)
+    zj.t[0, :, k:] = float('nan')                          # row padding must never be read as data
+    tin = ops.make_intrans(act_in) if act_in else None
+    wd, bd = dev(w), dev(b)
+    zl = ops.jet_linear_fwd(zj, tin, wd, 0, k, bd, None, 0, c)
+    sd = dev(slots) if masked else None
+    pooled, arg, zsel = ops.segmax_fwd_z(zl.t[0], act_pool, sd, n_seg, L, c)
+    # the rows the kernel selected (two maxima within one fp32 ulp may swap against the fp64 restatement: rare, and then
+    # either row is a correct arg-max of the fp32 forward; the gradient is checked for the rows actually selected)
+    sel = arg.cpu().long()
+    assert int((sel != ref_arg).sum()) <= 2
+    out = vals.gather(1, sel[:, None, :]).squeeze(1)
+    (out * gout.double()).sum().backward()
+    assert rel_l2(pooled[:, :c].cpu().double(), out.detach()) < 5e-6
+    assert ops.pool_layer_bwd_supported(n_seg, L, k, c, tin, zj.ld)
+    gd = dev(gout)
+    gw = torch.zeros_like(wd)
+    gb = torch.zeros(c, device='cuda')
+    ws = torch.empty(ops.pool_layer_bwd_workspace_bytes(n_seg, L, k, c), dtype=torch.uint8, device='cuda')
+    gzin = ops.pool_layer_bwd(gd, gd.stride(0), arg, zsel, act_pool, n_seg, L, c, zj, tin, k, wd, gw, gb, True, ws)
+    assert rel_l2(gw.cpu().double(), wr.grad) < GEMM_TOL
+    assert rel_l2(gb.cpu().double(), br.grad) < GEMM_TOL
+    assert rel_l2(gzin.t[0, :, :k].cpu().double(), zr.grad) < GEMM_TOL
+    # accumulation semantics of the parameter gradients, and bit-identical repeat (fixed summation order)
+    gw2 = torch.zeros_like(wd)
+    ops.pool_layer_bwd(gd, gd.stride(0), arg, zsel, act_pool, n_seg, L, c, zj, tin, k, wd, gw2, None, False, ws)
+    assert torch.equal(gw2, gw)
+    ops.pool_layer_bwd(gd, gd.stride(0), arg, zsel, act_pool, n_seg, L, c, zj, tin, k, wd, gw2, None, False, ws)
+    assert rel_l2(gw2.cpu().double(), 2 * wr.grad) < GEMM_TOL
+
+    # the same gradient through the dense form the sparse one replaces
+    gz = ops.segmax_bwd(gd, gd.stride(0), arg, zl.t[0], act_pool, n_seg, L, c)
+    dense = ops.jet_linear_bwd_dx(Jet(gz, c), wd, 0, zj, tin, None, 0, k, c)
+    assert rel_l2(gzin.t[0, :, :k].cpu().double(), dense.t[0, :, :k].cpu().double()) < GEMM_TOL
+
+
+def test_pool_compact_rows_carry_the_whole_gradient(ops):
+    """Long segments: the backward of a 2-layer encoder on the <= C selected rows per segment equals the dense one."""
+    from porous_cfd_b200 import engine
+    from porous_cfd_b200.ops import Jet
+    n_seg, L, k0, k1, c = 4, 700, 24, 96, 80
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n_seg * L, k0, generator=g)
+    lin0 = torch.nn.Linear(k0, k1)
+    lin1 = torch.nn.Linear(k1, c)
+    gout = torch.randn(n_seg, c, generator=g)
+    xr = x.double()
+    m0, m1 = lin0.double(), lin1.double()
+    out = torch.nn.functional.silu(m1(torch.nn.functional.silu(m0(xr)))).reshape(n_seg, L, c).max(dim=1).values
+    (out * gout.double()).sum().backward()
+    want = {id(p): p.grad.clone() for p in (m0.weight, m0.bias, m1.weight, m1.bias)}
+    lin0, lin1 = lin0.float().cuda(), lin1.float().cuda()
+    for p in (lin0.weight, lin0.bias, lin1.weight, lin1.bias):
+        p.grad = None
+    ctx = engine.StepContext(torch.device('cuda'))
+    params = [lin0.weight, lin0.bias, lin1.weight, lin1.bias]
+    for p in params:
+        ctx.grads[id(p)] = torch.zeros_like(p)
+    layers, pending = engine.mlp_chain([lin0, lin1], 'silu', True)
+    zj = Jet.empty(1, n_seg * L, k0, 'cuda'); zj.t[0, :, :k0].copy_(x)
+    zs = engine.chain_forward(ctx, layers, zj, L)
+    pooled, arg, zsel = ops.segmax_fwd_z(zs[-1].t[0], pending[0], None, n_seg, L, c)
+    gd = dev(gout)
+    assert not ops.pool_layer_bwd_supported(n_seg, L, k1, c, ops.make_intrans('silu'), zs[-2].ld)   # -> compaction path
+    engine.pool_backward(ctx, layers, zs, gd, gd.stride(0), arg, zsel, pending[0], n_seg, L, rows_per_geom=L)
+    torch.cuda.synchronize()
+    ref = [m0.weight, m0.bias, m1.weight, m1.bias]
+    for p, r in zip(params, ref):
+        assert rel_l2(ctx.grads[id(p)].cpu().double(), want[id(r)]) < GEMM_TOL

@@ -345,3 +345,18 @@ def test_pipelined_geometry_equals_eager(name):
         g1 = {k: p.grad for k, p in piped.named_parameters()}
         assert rel_l2(flat(g1, keys), flat(g0, keys)) < 1e-6, step
     assert len(piped.executor._graphs) == 1 and next(iter(piped.executor._graphs.values())).pipeline
+
+
+def test_steps_with_sparse_pool_backward_forced():
+    """PCFD_POOL_SPARSE=2 sends every pooled encoder layer the sparse kernels support through pool_layer_bwd (by default
+    only long neighbourhoods / thin inputs take it), =0 forces the dense form everywhere: the fixture and full-width
+    step comparisons must hold either way."""
+    import os
+    import subprocess
+    import sys
+    for mode in ('2', '0'):
+        env = dict(os.environ, PCFD_POOL_SPARSE=mode)
+        r = subprocess.run([sys.executable, '-m', 'pytest', os.path.abspath(__file__), '-q', '-x', '-m', 'gpu', '-k',
+                            'test_step_matches_reference_fixture or test_full_width_models_match_oracle'],
+                           env=env, capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, f'PCFD_POOL_SPARSE={mode}\n' + r.stdout[-3000:] + r.stderr[-2000:]
