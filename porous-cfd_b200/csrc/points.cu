@@ -377,8 +377,25 @@ __global__ void advance_seed_kernel(uint64_t* seed) { *seed = mix64(*seed); }
 
 using namespace pcfd;
 
+extern "C" int pcfd_fps_bucket_supported(int32_t n_geom, int32_t n, int32_t dims);
+extern "C" size_t pcfd_fps_bucket_workspace_bytes(int32_t n_geom, int32_t n, int32_t dims);
+extern "C" int pcfd_fps_bucket(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+// point sets from this size on take the bucketed sampler (fps_bucket.cu); PCFD_FPS_BUCKET_MIN overrides (0 = never)
+static int fps_bucket_min() {
+  static int v = -1;
+  if (v < 0) { const char* ev = getenv("PCFD_FPS_BUCKET_MIN"); v = ev ? atoi(ev) : 4096; }
+  return v;
+}
+static bool fps_use_bucket(int32_t n_geom, int32_t n, int32_t dims) {
+  const int mn = fps_bucket_min();
+  return mn > 0 && n >= mn && pcfd_fps_bucket_supported(n_geom, n, dims);
+}
+
 extern "C" size_t pcfd_fps_workspace_bytes(int32_t n_geom, int32_t n, int32_t dims) {
   if (n_geom <= 0 || n <= 0) return 0;
+  if (fps_use_bucket(n_geom, n, dims)) return pcfd_fps_bucket_workspace_bytes(n_geom, n, dims);
   // the register / cluster kernels (n <= 65536) need none; the size is reported all the same so that the fall-back
   // (PCFD_FPS_CLUSTER=0) keeps working with the caller's buffer
   return (size_t)n * (dims + 1) * sizeof(float) > 220 * 1024 ? (size_t)n_geom * n * sizeof(float) : 0;
@@ -387,6 +404,9 @@ extern "C" size_t pcfd_fps_workspace_bytes(int32_t n_geom, int32_t n, int32_t di
 extern "C" int pcfd_fps_ws(const float* pos, int32_t n_geom, int32_t n, int32_t dims, int32_t m, int64_t* idx_out,
                            void* workspace, size_t workspace_bytes, void* stream) {
   if (!pos || !idx_out || n_geom <= 0 || n <= 0 || m <= 0 || m > n || (dims != 2 && dims != 3)) return PCFD_ERR_ARG;
+  // large point sets: exact bucketed sampling (needs the caller's workspace; pcfd_fps without one keeps the plain kernels)
+  if (workspace != nullptr && fps_use_bucket(n_geom, n, dims))
+    return pcfd_fps_bucket(pos, n_geom, n, dims, m, idx_out, workspace, workspace_bytes, stream);
   // The cluster kernel is bit-exact (tests run it with PCFD_FPS_CLUSTER=1) but NOT the default: measured on a B200, the
   // per-sample cluster barrier + distributed-shared-memory reads cost more than the shorter per-thread chain saves
   // (windbreaks 8192 -> 4096 points, 2 geometries: 8.8 ms against 5.3 ms for one CTA per geometry; 16384 points: 25 vs 18).

@@ -86,6 +86,61 @@ print("cluster fps ok")
     assert r.returncode == 0 and 'cluster fps ok' in r.stdout, r.stderr[-2000:]
 
 
+def _surface_points(nb, n, d, gen):
+    """Points on a few thin shells / curves with exact duplicates and a grid-aligned patch: what boundary point sets look
+    like (highly non-uniform in the bounding box), plus the tie / zero-distance cases of the bucketed sampler."""
+    t = torch.rand(nb, n, generator=gen) * 6.2831853
+    r = 0.3 + 0.5 * (torch.rand(nb, n, generator=gen) > 0.5).float()
+    pos = torch.zeros(nb, n, d)
+    pos[..., 0] = r * torch.cos(t)
+    pos[..., 1] = r * torch.sin(t)
+    if d == 3:
+        pos[..., 2] = torch.round(torch.rand(nb, n, generator=gen) * 8) / 8 - 0.5
+    q = n // 8
+    pos[:, :q] = torch.round(pos[:, :q] * 16) / 16                      # lattice points: many exact ties
+    pos[:, q:2 * q] = pos[:, :q]                                        # exact duplicates
+    return pos
+
+
+@pytest.mark.parametrize('shape', [(2, 4096, 3, 0.5), (3, 5000, 2, 0.25), (2, 16384, 3, 0.5), (1, 65536, 2, 0.5),
+                                   (1, 40000, 3, 0.05)])
+@pytest.mark.parametrize('kind', ['uniform', 'surface'])
+def test_fps_bucketed_bit_exact(ops, shape, kind):
+    """Large point sets take the bucketed sampler (fps_bucket.cu): same selection, in the same order, as the plain
+    algorithm of the oracle -- including ties and duplicates (lowest ORIGINAL index wins although storage is permuted)."""
+    nb, n, d, ratio = shape
+    g = torch.Generator().manual_seed(n + d)
+    pos = torch.rand(nb, n, d, generator=g) * 2 - 1 if kind == 'uniform' else _surface_points(nb, n, d, g)
+    want = pyg_restate.fps(pos.reshape(-1, d), torch.arange(nb).repeat_interleave(n), ratio)
+    got = ops.fps(dev(pos), ratio).cpu().flatten()
+    assert torch.equal(got, want)
+
+
+def test_fps_bucketed_equals_plain_kernels(ops):
+    """The same inputs through the plain one-CTA kernels (PCFD_FPS_BUCKET_MIN=0, fresh process) and the bucketed path."""
+    import os
+    import subprocess
+    import sys
+    code = f'''
+import sys, torch
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import pcfd_import; pcfd_import.load()
+from porous_cfd_b200 import ops
+g = torch.Generator().manual_seed(11)
+pos = torch.rand(2, 8192, 3, generator=g) * 2 - 1
+torch.save(ops.fps(pos.cuda(), 0.5).cpu(), sys.argv[1])
+'''
+    import tempfile
+    outs = []
+    for mn in ('0', '4096'):
+        with tempfile.NamedTemporaryFile(suffix='.pt') as f:
+            r = subprocess.run([sys.executable, '-c', code, f.name], env=dict(os.environ, PCFD_FPS_BUCKET_MIN=mn),
+                               capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(torch.load(f.name))
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_fps_ties_pick_lowest_index(ops):
     pos = torch.tensor([[[0., 0.], [1., 0.], [1., 0.], [0., 1.], [0., 1.], [0.5, 0.5]]])
     assert ops.fps(dev(pos), 0.5).cpu().flatten().tolist() == [0, 1, 3]
