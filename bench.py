@@ -219,7 +219,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--engine', type=int, default=None,
-                    help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 1 = tcgen05 with thread-staged operands, 0 = fp32 FFMA')
+                    help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 0 = the generic fp32 FFMA reference engine')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--sync-loss', action='store_true', help='end-to-end leg: blocking float(loss) every step instead of the delayed read')
@@ -260,8 +260,9 @@ def main():
     W, K = max(3, args.warmup), max(1, args.steps)
     if args.engine is not None:
         ops.set_gemm_engine(args.engine)
-    engine = _lib.load().pcfd_get_gemm_engine()
-    engine_name = {0: 'fp32 FFMA', 1: 'tcgen05 3xTF32 (thread-staged operands)', 2: 'TMA + tcgen05 3xTF32, warp-specialised'}[engine]
+    engine = 0 if ops.FORCE_FFMA else 2
+    engine_name = {0: 'fp32 FFMA (reference engine)', 2: 'TMA + tcgen05 3xTF32, warp-specialised'}[engine]
+    ops.AUDIT = True          # wide layers must run on the tensor cores: fallbacks are recorded and reported
 
     model, spec = make_model(device)
     trainer = FlatAdamTrainer(model)

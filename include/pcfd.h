@@ -46,10 +46,10 @@ enum { PCFD_ACT_NONE = 0, PCFD_ACT_SILU = 1, PCFD_ACT_TANH = 2 };
 /* ABI version, and the compute capability (major*10+minor) of the current device. */
 int pcfd_abi_version(void);
 int pcfd_device_arch(int* cc_out_host);
-/* Which engine executes the jet GEMMs: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 with thread-staged operands,
- * 2 = warp-specialised TMA + tcgen05 3xTF32 (default of the Python host). */
-int pcfd_set_gemm_engine(int engine);
-int pcfd_get_gemm_engine(void);
+/* The library holds NO mutable state and is re-entrant: every entry point is a function of its arguments, work goes to
+ * the stream passed in, the device is the caller's current device.  (Per-device records of which kernels already have
+ * their shared-memory attribute set are idempotent caches behind atomics; environment switches named in DESIGN.md are
+ * read once.) */
 
 /* ------------------------------------------------------------------------------------------
  * Input transform of a jet layer.  The reference applies activation / dropout / branch scaling
@@ -116,6 +116,37 @@ int pcfd_jet_linear_bwd_dw(const float* gzout, int64_t gzout_plane_stride, int32
                            float* gw, int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec,
                            int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Which kernel family the three entry points above execute for a given call -- a pure query, nothing is launched:
+ * PCFD_ENGINE_TCGEN05 (warp-specialised TMA + tcgen05 3xTF32 kernels, the product path for every wide layer),
+ * PCFD_ENGINE_THIN (fp32 streaming kernels for first / last layers and per-geometry rows, where no tensor-core tile
+ * fits) or PCFD_ENGINE_FFMA (the generic fp32 CUDA-core engine: misaligned operands, fewer than 256 rows, ...).
+ * pass: 0 forward (a = zin, b = zout), 1 dX (a = gzout, b = zin), 2 dW (a = gzout, b = zin).  Callers that expect their
+ * wide layers on the tensor cores assert on the answer (bench.py, tests) instead of finding a slow fallback later.
+ */
+enum { PCFD_ENGINE_FFMA = 0, PCFD_ENGINE_THIN = 1, PCFD_ENGINE_TCGEN05 = 2 };
+int pcfd_jet_linear_engine(int32_t pass, const float* a, int64_t a_plane_stride, int32_t lda, const float* w, int32_t ldw,
+                           const float* b, int64_t b_plane_stride, int32_t ldb, const pcfd_intrans_t* tin_host,
+                           int32_t has_gescale, int32_t cj, int64_t rows, int32_t k, int32_t n);
+/*
+ * The generic fp32 CUDA-core engine under its own names, same arguments as pcfd_jet_linear_{fwd,bwd_dx,bwd_dw}: an
+ * independent implementation of the same layer that tests and scripts/bench_layers.py compare the tensor-core kernels
+ * with (any shape, any alignment).
+ */
+int pcfd_ffma_jet_linear_fwd(const float* zin, int64_t zin_plane_stride, int32_t ldzin, const pcfd_intrans_t* tin_host,
+                             const float* w, int32_t ldw, const float* bias, const float* cvec, int32_t ldcvec,
+                             float* zout, int64_t zout_plane_stride, int32_t ldzout,
+                             int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n, void* stream);
+int pcfd_ffma_jet_linear_bwd_dx(const float* gzout, int64_t gzout_plane_stride, int32_t ldgzout, const float* w, int32_t ldw,
+                                const float* zin, int64_t zin_plane_stride, int32_t ldzin, const pcfd_intrans_t* tin_host,
+                                float* gzin, int64_t gzin_plane_stride, int32_t ldgzin, float* gescale, int32_t ldgescale,
+                                int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n, void* stream);
+int pcfd_ffma_jet_linear_bwd_dw(const float* gzout, int64_t gzout_plane_stride, int32_t ldgzout,
+                                const float* zin, int64_t zin_plane_stride, int32_t ldzin, const pcfd_intrans_t* tin_host,
+                                float* gw, int32_t ldgw, float* gbias, float* gcvec, int32_t ldgcvec,
+                                int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Segmented max with arg-max: out[s][c] = max_{valid slots j} act(z[s*seg_len + j][c]).
@@ -288,6 +319,21 @@ int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n_rows, int3
                          const int64_t* internal_ids, int64_t ni,
                          const float* y_int, int64_t y_plane_stride, int32_t ldy,
                          const pcfd_residual_params_t* prm_host, float* fields, void* stream);
+
+/*
+ * The loss modules on EXPLICIT tensors, for callers that hold the derivative tensors themselves (the reference's
+ * predict_step, models/model_base.py:241-246, and evaluation code): ContinuityLoss[Standardized].func
+ * (models/losses.py:154-156, 177-182) -> div [rows]; MomentumLoss{Manufactured,Fixed,Variable}.func (:209-217,
+ * :256-266, :301-311) -> momentum [rows][D].  Dense row-major inputs: u [rows][D], jac / lap [rows][D][D]
+ * (jac[i][j] = dU_i/dx_j, lap[i][j] = d2U_i/dx_j2), p_grad [rows][D], zone [rows] (cellToRegion), and per kind:
+ * VARIABLE dcoef / fcoef [rows][D] (normalised d, f), MANUFACTURED fcoef [rows][D] (the forcing term, may be NULL).
+ * Either output may be NULL.  Scalers / constants come from prm_host (column indices and weights are ignored).
+ */
+int pcfd_residual_eval(const float* u, const float* jac, const float* lap, const float* p_grad, const float* zone,
+                       const float* dcoef, const float* fcoef, int64_t rows, const pcfd_residual_params_t* prm_host,
+                       float* momentum, float* div, void* stream);
+/* out[c] = mean_r x[r][c]^2: vector_loss(res, 0, mse_loss) / mse_loss(res, 0) of the modules' forward (models/losses.py:10-20). */
+int pcfd_mean_squares(const float* x, int64_t rows, int32_t cols, float* out, void* stream);
 
 /* RelobraloScaler.forward (models/losses.py:93-124) on the device: `losses` = the n unscaled loss terms of this
  * step (out[0..n) of a residual pass), the three buffers are the module's registered buffers, `step` a device

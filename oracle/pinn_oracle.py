@@ -65,15 +65,21 @@ def rows(data: Tensor, ids: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------
 
 def mlp(x: Tensor, p: dict, prefix: str, n_layers: int, act, last_activation: bool = True,
-        dropout=None, training: bool = False, fmt: str = 'Linear {}') -> Tensor:
-    """models/modules.py:23-53: Linear -> act (-> Dropout) per layer; keys '<prefix>Linear k.*'."""
+        dropout=None, training: bool = False, fmt: str = 'Linear {}', dropout_fn=None, site0: int = 0) -> Tensor:
+    """models/modules.py:23-53: Linear -> act (-> Dropout) per layer; keys '<prefix>Linear k.*'.
+    `dropout_fn(x, p, site)` (oracle/dropout_hash.CounterDropout) replaces torch's Philox mask by the CUDA path's
+    counter-hash mask in training mode; layer k of this stack is layer site0 + k of the model's point chain, its
+    dropped activations are consumed by layer site0 + k + 1."""
     for k in range(n_layers):
         name = prefix + fmt.format(k)
         x = F.linear(x, p[name + '.weight'], p[name + '.bias'])
         if k < n_layers - 1 or last_activation:
             x = act(x)
         if dropout is not None and dropout[k] > 0:
-            x = F.dropout(x, dropout[k], training)
+            if training and dropout_fn is not None:
+                x = dropout_fn(x, dropout[k], site0 + k + 1)
+            else:
+                x = F.dropout(x, dropout[k], training)
     return x
 
 
@@ -124,7 +130,7 @@ def set_abstraction_stack(x: Tensor, pos: Tensor, p: dict, prefix: str, spec: di
 # --------------------------------------------------------------------------------------
 
 def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain: dict,
-            training: bool = False) -> Tensor:
+            training: bool = False, dropout_fn=None) -> Tensor:
     kind = spec['kind']
     act = ACTS[spec['activation']]
     n = pts.shape[-2]
@@ -139,7 +145,7 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
         g = max_over_points(g)
         seg_in = torch.cat([local, g.repeat(1, n, 1)], dim=-1)
         return mlp(seg_in, p, 'decoder.', len(spec['seg_layers']) - 1, act, False,
-                   spec.get('seg_dropout'), training)
+                   spec.get('seg_dropout'), training, dropout_fn=dropout_fn, site0=len(spec['fe_local_layers']) - 1)
     if kind in ('PipnFoamPp', 'PipnManufacturedPorousPp'):
         # models/pipn/pipn_foam.py:148-161, pipn_baseline.py:104-119 (feature order differs!)
         bnd = rows(data, domain['boundary'])
@@ -152,7 +158,7 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
                                    'max_neighbors': spec.get('max_neighbors', 64)}, act)
         seg_in = torch.cat([local, g.repeat(1, n, 1)], dim=-1)
         return mlp(seg_in, p, 'decoder.', len(spec['seg_layers']) - 1, act, False,
-                   spec.get('seg_dropout'), training)
+                   spec.get('seg_dropout'), training, dropout_fn=dropout_fn, site0=len(spec['fe_local_layers']) - 1)
     if kind in ('PiGano', 'PiGanoPp'):
         # models/pi_gano/pi_gano.py:49-69, pi_gano_pp.py:62-82, base.py:60-73
         par = []
@@ -182,7 +188,10 @@ def forward(spec: dict, p: dict, pts: Tensor, data: Tensor, labels: dict, domain
             h = act(F.linear(h, p[f'neural_ops.Operator {k}.linear.0.weight'],
                              p[f'neural_ops.Operator {k}.linear.0.bias']))
             if spec['operator_dropout'][k] > 0:
-                h = F.dropout(h, spec['operator_dropout'][k], training)
+                if training and dropout_fn is not None:     # operator k is layer (n_encoder + k) of the point chain
+                    h = dropout_fn(h, spec['operator_dropout'][k], len(spec['local_layers']) - 1 + k + 1)
+                else:
+                    h = F.dropout(h, spec['operator_dropout'][k], training)
             h = h * pe
         return F.linear(h, p['reduction.weight'], p['reduction.bias'])
     raise KeyError(kind)
@@ -258,7 +267,7 @@ def momentum_residual(spec: dict, internal: Tensor, labels: dict, u: Tensor, jac
 
 
 def training_step(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
-                  laplacian: str = 'reference', training: bool = False) -> dict:
+                  laplacian: str = 'reference', training: bool = False, dropout_fn=None) -> dict:
     """One training step as models/model_base.py:182-218 performs it.
 
     laplacian='reference' reproduces the call as written (`get_laplacian(points, U)`);
@@ -270,7 +279,7 @@ def training_step(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
     boundary = rows(data, domain['boundary'])
     pts = field(internal, labels, 'C').detach().clone().requires_grad_(True)
     all_pts = torch.cat([pts, field(boundary, labels, 'C')], dim=-2)
-    y = forward(spec, p, all_pts, data, labels, domain, training)
+    y = forward(spec, p, all_pts, data, labels, domain, training, dropout_fn)
     out_labels = {**{n: None for n in ['Ux', 'Uy', 'Uz'][:dims]}, 'p': None, 'U': ['Ux', 'Uy', 'Uz'][:dims]}
 
     y_int, y_bnd = rows(y, domain['internal']), rows(y, domain['boundary'])
@@ -314,10 +323,10 @@ def training_step(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
 
 
 def step_with_grads(spec: dict, p: dict, data: Tensor, labels: dict, domain: dict,
-                    laplacian: str = 'reference', training: bool = False) -> dict:
+                    laplacian: str = 'reference', training: bool = False, dropout_fn=None) -> dict:
     """training_step + loss.backward(): returns the step outputs and {key: grad} for every parameter."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
-    out = training_step(spec, leaves, data, labels, domain, laplacian, training)
+    out = training_step(spec, leaves, data, labels, domain, laplacian, training, dropout_fn)
     out['loss'].backward()
     out['grads'] = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
     return out

@@ -16,7 +16,7 @@ ACT_CODES = {None: ACT_NONE, 'none': ACT_NONE, 'silu': ACT_SILU, 'tanh': ACT_TAN
 LOSS_KINDS = {'manufactured': 0, 'fixed': 1, 'variable': 2}
 LAP_MODES = {'reference': 0, 'true': 1}
 LOSS_OUT_FLOATS = 48
-DEFAULT_ENGINE = 2   # jet GEMMs: 2 = warp-specialised TMA + tcgen05 3xTF32, 1 = tcgen05 3xTF32 (thread-staged operands), 0 = fp32 FFMA (CUDA cores)
+ENGINE_FFMA, ENGINE_THIN, ENGINE_TCGEN05 = 0, 1, 2   # answers of pcfd_jet_linear_engine
 
 ERRORS = {1: 'bad argument (shape / null pointer / unsupported channel count)', 2: 'misaligned pointer',
           3: 'workspace too small', 4: 'device is not sm_100 (no fallback path exists)'}
@@ -48,8 +48,6 @@ _IT = C.POINTER(InTrans)
 SIGNATURES = {
     'pcfd_abi_version': (C.c_int, []),
     'pcfd_device_arch': (C.c_int, [C.POINTER(C.c_int)]),
-    'pcfd_set_gemm_engine': (C.c_int, [C.c_int]),
-    'pcfd_get_gemm_engine': (C.c_int, []),
     'pcfd_jet_linear_fwd': (C.c_int, [_P, _I64, _I32, _IT, _P, _I32, _P, _P, _I32, _P, _I64, _I32,
                                       _I32, _I64, _I64, _I32, _I32, _P]),
     'pcfd_jet_linear_bwd_dx': (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I64, _I32, _IT, _P, _I64, _I32, _P, _I32,
@@ -57,6 +55,13 @@ SIGNATURES = {
     'pcfd_jet_linear_bwd_dw_workspace_bytes': (_SZ, [_I32, _I64, _I64, _I32, _I32]),
     'pcfd_jet_linear_bwd_dw': (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _IT, _P, _I32, _P, _P, _I32,
                                          _I32, _I64, _I64, _I32, _I32, _P, _SZ, _P]),
+    'pcfd_jet_linear_engine': (C.c_int, [_I32, _P, _I64, _I32, _P, _I32, _P, _I64, _I32, _IT, _I32, _I32, _I64, _I32, _I32]),
+    'pcfd_ffma_jet_linear_fwd': (C.c_int, [_P, _I64, _I32, _IT, _P, _I32, _P, _P, _I32, _P, _I64, _I32,
+                                           _I32, _I64, _I64, _I32, _I32, _P]),
+    'pcfd_ffma_jet_linear_bwd_dx': (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I64, _I32, _IT, _P, _I64, _I32, _P, _I32,
+                                              _I32, _I64, _I64, _I32, _I32, _P]),
+    'pcfd_ffma_jet_linear_bwd_dw': (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _IT, _P, _I32, _P, _P, _I32,
+                                              _I32, _I64, _I64, _I32, _I32, _P, _SZ, _P]),
     'pcfd_segmax_fwd': (C.c_int, [_P, _I32, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P]),
     'pcfd_segmax_fwd_z': (C.c_int, [_P, _I32, _I32, _P, _I64, _I32, _I32, _P, _I32, _P, _P, _I32, _P]),
     'pcfd_segmax_bwd': (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _I64, _I32, _I32, _P, _I32, _P]),
@@ -81,6 +86,8 @@ SIGNATURES = {
     'pcfd_residual_loss_w': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
                                        C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
+    'pcfd_residual_eval': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(ResidualParams), _P, _P, _P]),
+    'pcfd_mean_squares': (C.c_int, [_P, _I64, _I32, _P, _P]),
     'pcfd_adam_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     'pcfd_relobralo_update': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F, _F, _F, _F, C.c_uint64, _P, _P]),
     'pcfd_sdf_feature': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
@@ -114,8 +121,6 @@ def load() -> C.CDLL:
         fn.restype, fn.argtypes = res, args
     if lib.pcfd_abi_version() != 1:
         raise PcfdError('libpcfd_sm100.so ABI version mismatch; rebuild')
-    engine = int(os.environ.get('PCFD_ENGINE', str(DEFAULT_ENGINE)))
-    check(lib.pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')
     _lib = lib
     return lib
 

@@ -38,8 +38,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == d:
         return LIB
     defines = []
-    if os.path.exists(os.path.join(CSRC, 'jet_linear_tc.cu')):
-        defines.append('-DPCFD_HAVE_TC')
     objs = []
     procs = []
     for src in sources():

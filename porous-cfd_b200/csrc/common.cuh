@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <utility>
 
@@ -35,6 +36,24 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-(kernel, device) attribute: set it the first time a device sees the
+// kernel (or needs more than before).  The record is an idempotent cache, one atomic per device: safe from several host
+// threads and with several devices in one process (a plain `static bool configured` is neither).
+template <auto Kernel>
+inline cudaError_t ensure_dyn_smem(int bytes) {
+  static std::atomic<int> have[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorInvalidDevice;
+  std::atomic<int>& h = have[dev & 63];
+  if (h.load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) {
+    int cur = h.load(std::memory_order_relaxed);
+    while (cur < bytes && !h.compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+  }
+  return e;
 }
 
 // ---- programmatic dependent launch -----------------------------------------------------------------

@@ -479,11 +479,9 @@ static int launch_dw(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
   const int stage_bytes = 2 * (p.mt * 4 + p.ntl * NT / 32) * (CJ * R * 128);
   const int smem = p.stages * stage_bytes + 1024;
   if (smem > DW_SMEM_MAX + 1024) return PCFD_ERR_ARG;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(ws_dw_kernel<CJ, R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_MAX + 1024);
+  {
+    const cudaError_t e = ensure_dyn_smem<ws_dw_kernel<CJ, R, NT>>(DW_SMEM_MAX + 1024);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
-    configured = DW_SMEM_MAX + 1024;
   }
   dim3 grid((unsigned)(p.passes_n * p.passes_k), (unsigned)p.splits);
   const cudaError_t le = launch_pdl(ws_dw_kernel<CJ, R, NT>, grid, dim3(DW_THREADS), (size_t)smem, st, tmG, tmZ, a);
@@ -512,11 +510,9 @@ static int launch_dw1(const float* gzout, int ldgzout, const float* zin, int ldz
   if (smem < 4 * 4 * 128 * 4) smem = 4 * 4 * 128 * 4;          // the column sums of the groups reuse the ring
   smem += 1024;
   if (smem > DW_SMEM_MAX + 1024) return PCFD_ERR_ARG;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ws_dw1_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_MAX + 1024);
+  {
+    const cudaError_t e = ensure_dyn_smem<ws_dw1_kernel<R, NT>>(DW_SMEM_MAX + 1024);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
-    configured = true;
   }
   dim3 grid((unsigned)(p.passes_n * p.passes_k), (unsigned)p.splits);
   const cudaError_t le = launch_pdl(ws_dw1_kernel<R, NT>, grid, dim3(DW1_THREADS), (size_t)smem, st, tmG, tmZ, a);

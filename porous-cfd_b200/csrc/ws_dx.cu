@@ -427,11 +427,9 @@ static int launch_dx(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("PCFD_WS_DEBUG"); dbg = e ? atoi(e) : 0; }
   a.dbg = dbg;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ws_dx_kernel<CJ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {
+    const cudaError_t e = ensure_dyn_smem<ws_dx_kernel<CJ, NT>>(SMEM);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
-    configured = true;
   }
   const int total = a.row_tiles * a.k_passes;
   const int grid = total < num_sms() ? total : num_sms();

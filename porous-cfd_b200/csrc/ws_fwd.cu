@@ -340,11 +340,9 @@ static int launch_fwd(const float* zin, int64_t zin_ps, int ldzin, const float* 
   a.dbg = dbg;
   a.row_tiles = (int)((a.rows + POINTS - 1) / POINTS);
   a.n_passes = (a.n + NT - 1) / NT;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ws_fwd_kernel<CJ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {
+    const cudaError_t e = ensure_dyn_smem<ws_fwd_kernel<CJ, NT>>(SMEM);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
-    configured = true;
   }
   const int total = a.row_tiles * a.n_passes;
   const int grid = total < num_sms() ? total : num_sms();

@@ -333,11 +333,9 @@ static int launch_fwd1(const float* zin, int ldzin, const float* w, int ldw, flo
   a.vec_const = (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.cvec) & 15) == 0 && a.ldcvec % 4 == 0;
   a.row_tiles = (int)((a.rows + 127) / 128);
   a.n_passes = (a.n + NT - 1) / NT;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ws_fwd1_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  {
+    const cudaError_t e = ensure_dyn_smem<ws_fwd1_kernel<NT>>(SMEM);
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
-    configured = true;
   }
   const int total = a.row_tiles * a.n_passes;
   const int grid = total < num_sms() ? total : num_sms();

@@ -68,6 +68,7 @@ class StepContext:
         # fork independent work to a side stream (off: one stream, for per-kernel timing / ordered ncu launch lists)
         self.overlap = os.environ.get('PCFD_NO_OVERLAP', '0') != '1'
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
+        self.retired: list = []
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.training = False
         self.grads: dict[int, Tensor] = {}
@@ -78,6 +79,9 @@ class StepContext:
         if self.workspace.numel() < nbytes:
             if self.side_stream is not None:      # dW kernels on the side stream may still read the old buffer
                 self.side_stream.synchronize()
+            # a captured step graph has the address of the workspace it was recorded with baked in: superseded buffers
+            # stay allocated (they are a few MB) so that replaying an older graph never writes into freed memory
+            self.retired.append(self.workspace)
             self.workspace = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
 
     def grad(self, p: Optional[nn.Parameter]) -> Optional[Tensor]:
@@ -419,6 +423,12 @@ class PinnExecutor:
         self._graphs: dict = {}
         self._seen: set = set()
 
+    def reset_graphs(self) -> None:
+        """Forget the captured step graphs (their kernels hold loss weights, scaler values and buffer addresses by
+        value): the next call of a signature runs eagerly, the one after re-captures."""
+        self._graphs.clear()
+        self._seen.clear()
+
     # ---- helpers --------------------------------------------------------------------------
     def _cols(self, labels: dict, name: str):
         keys = list(labels.keys())
@@ -580,6 +590,23 @@ class PinnExecutor:
         zs = chain_forward(ctx, plan['point_layers'], z0, n, escale, cvecs, salt_base=100)
         ops.end_step()
         return zs[-1].values().reshape(b, n, d + 1)
+
+    def forward_jets(self, points: Tensor, data: Tensor, labels: dict, domain: dict, order: int = 2) -> Jet:
+        """Model.forward(autograd_points, x) with its spatial derivatives: the output jet [cj][B*N][ld] at ALL `points`
+        (B, N, D): plane 0 the predictions, planes 1..D d/dx_k, planes D+1..2D d2/dx_k2 (order 2).  This is what the
+        reference obtains from autograd.grad sweeps over the points (models/model_base.py:11-53); served to
+        get_jacobian / get_laplacian / calculate_gradients through model_base._JetForward."""
+        plan, ctx = self.plan, self.ctx
+        ctx.training = self.model.training
+        b, n, d = points.shape
+        points = points.detach().contiguous().float()
+        cj = 1 + order * d
+        ops.begin_step()
+        cvecs, escale, _ = self._encode(data, labels, domain, None, None, points)
+        z0 = ops.seed_jet(points, None, n, list(range(d)), cj)
+        zs = chain_forward(ctx, plan['point_layers'], z0, n, escale, cvecs, salt_base=100)
+        ops.end_step()
+        return zs[-1]
 
     def graphed_step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
                      next_batch=None) -> StepResult:

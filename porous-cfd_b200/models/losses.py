@@ -15,7 +15,8 @@ from ..dataset.foam_dataset import Normalizer, StandardScaler
 class LossScaler(nn.Module):
     """Identity weighting (reference models/losses.py:23-36)."""
 
-    def weights(self, n_terms: int) -> list[float]:
+    def weight_list(self, n_terms: int) -> list[float]:
+        """The static weights the residual kernel applies, one per loss term."""
         return [1.0] * n_terms
 
     def forward(self, model, losses: Tensor) -> Tensor:
@@ -31,20 +32,20 @@ class FixedLossScaler(LossScaler):
         w = list(loss_weights['continuity']) + list(loss_weights['momentum']) + list(loss_weights['boundary'])
         if 'observations' in loss_weights:
             w += list(loss_weights['observations'])
-        self.weights_t = torch.tensor(w, dtype=torch.float)
+        self.weights = torch.tensor(w, dtype=torch.float)      # tensor attribute, as in the reference (:53)
 
-    def weights(self, n_terms: int) -> list[float]:
-        w = [float(v) for v in self.weights_t.tolist()]
+    def weight_list(self, n_terms: int) -> list[float]:
+        w = [float(v) for v in self.weights.tolist()]
         if len(w) < n_terms:
             raise ValueError(f'FixedLossScaler holds {len(w)} weights, the step produces {n_terms} loss terms')
         return w[:n_terms]
 
     def forward(self, model, losses: Tensor) -> Tensor:
-        return losses * self.weights_t.to(losses.device)
+        return losses * self.weights.to(losses.device)
 
     def to(self, *args, **kwargs):
         super().to(*args, **kwargs)
-        self.weights_t = self.weights_t.to(*args, **kwargs)
+        self.weights = self.weights.to(*args, **kwargs)
         return self
 
 
@@ -76,7 +77,7 @@ class RelobraloScaler(LossScaler):
     def set_batch_size(self, batch_size: int) -> None:
         self.batch_size = int(batch_size)
 
-    def weights(self, n_terms: int) -> list[float]:
+    def weight_list(self, n_terms: int) -> list[float]:
         return [1.0] * n_terms     # the static slot of the residual parameters; the live weights are on the device
 
     def device_state(self, device):
@@ -108,8 +109,18 @@ class LossLogger:
             self.module.log(label, value, on_step=False, on_epoch=True, batch_size=batch_size)
 
 
+def _vec(x, n):
+    t = torch.as_tensor(x, dtype=torch.float64).flatten().cpu()
+    if t.numel() == 1:
+        t = t.repeat(n)
+    return [float(v) for v in t[:n]]
+
+
 class _ResidualSpec(nn.Module):
-    """Common holder: which residual variant the kernel evaluates and with which constants."""
+    """Common part of the loss modules: the physics constants / scalers, and `func` / `forward` on explicit tensors
+    through pcfd_residual_eval + pcfd_mean_squares (csrc/residual_eval.cu).  The training step does not call these: it
+    evaluates residual, losses and gradient in the fused pcfd_residual_loss, configured from the same attributes by
+    `PorousPinnBase.residual_params`."""
     kind = 'fixed'
 
     def __init__(self):
@@ -117,20 +128,67 @@ class _ResidualSpec(nn.Module):
         self.nu, self.d, self.f = 0.0, 0.0, 0.0
         self.u_scaler = self.points_scaler = self.p_scaler = self.d_scaler = self.f_scaler = None
 
-    def func(self, *args):
-        raise NotImplementedError('per-point residual fields come from PorousPinnBase.predict_step with '
-                                  'verbose_predict=True (pcfd_residual_fields); the loss modules hold constants only')
+    def eval_params(self, dims: int):
+        """pcfd_residual_params_t for the explicit-tensor kernel (column indices and weights unused)."""
+        from .._lib import LOSS_KINDS, ResidualParams
+        prm = ResidualParams()
+        prm.dims, prm.loss_kind, prm.lap_mode, prm.enable_data_loss = dims, LOSS_KINDS[self.kind], 1, 0
+        prm.nu, prm.d, prm.f = float(self.nu), float(self.d), float(self.f)
+        ones, zeros = [1.0] * 3, [0.0] * 3
+        prm.c_std[:], prm.u_std[:], prm.u_mean[:] = ones, ones, zeros
+        prm.p_std, prm.p_mean = 1.0, 0.0
+        if self.kind != 'manufactured':
+            prm.c_std[:dims] = _vec(self.points_scaler.std, dims)
+            prm.u_std[:dims], prm.u_mean[:dims] = _vec(self.u_scaler.std, dims), _vec(self.u_scaler.mean, dims)
+            if self.p_scaler is not None:
+                prm.p_std, prm.p_mean = _vec(self.p_scaler.std, 1)[0], _vec(self.p_scaler.mean, 1)[0]
+        if self.kind == 'variable':
+            prm.d_min[:dims], prm.d_range[:dims] = _vec(self.d_scaler.min, dims), _vec(self.d_scaler.range, dims)
+            prm.f_min[:dims], prm.f_range[:dims] = _vec(self.f_scaler.min, dims), _vec(self.f_scaler.range, dims)
+        return prm
 
-    def forward(self, *args):
-        raise NotImplementedError('losses are evaluated inside PorousPinnBase.training_step by pcfd_residual_loss')
+
+class _Continuity(_ResidualSpec):
+    def func(self, jacobian: Tensor) -> Tensor:
+        """div = sum_i jac[..., i, i] * u_std_i / x_std_i  (..., D, D) -> (...)."""
+        from .. import ops
+        return ops.residual_eval(self.eval_params(jacobian.shape[-1]), jacobian.detach(), want_momentum=False,
+                                 want_div=True)[1]
+
+    def forward(self, *args) -> Tensor:
+        """mse of the divergence against zero: a 0-d tensor."""
+        from .. import ops
+        return ops.mean_squares(self.func(*args).reshape(-1, 1))[0]
 
 
-class ContinuityLoss(_ResidualSpec):
+class _Momentum(_ResidualSpec):
+    def func(self, internal_input, u: Tensor, u_jac: Tensor, u_laplace: Tensor, p_grad: Tensor) -> Tensor:
+        """Momentum residual (..., D) from the internal-domain inputs (FoamData with cellToRegion [, d, f]), the
+        velocity, its Jacobian and Laplacian terms, and the pressure gradient."""
+        from .. import ops
+        dims = u.shape[-1]
+        zone = internal_input['cellToRegion']
+        dcoef = fcoef = None
+        if self.kind == 'variable':
+            dcoef, fcoef = internal_input['d'], internal_input['f']
+        elif self.kind == 'manufactured':
+            fcoef = internal_input['f']
+        det = lambda t: None if t is None else t.detach()
+        return ops.residual_eval(self.eval_params(dims), det(u_jac), det(u), det(u_laplace), det(p_grad), det(zone),
+                                 det(dcoef), det(fcoef))[0]
+
+    def forward(self, *args) -> Tensor:
+        """Per-component mean of the squared residual: (D,)."""
+        from .. import ops
+        return ops.mean_squares(self.func(*args))
+
+
+class ContinuityLoss(_Continuity):
     """div U = 0 on raw outputs (reference models/losses.py:149-164)."""
     kind = 'manufactured'
 
 
-class ContinuityLossStandardized(_ResidualSpec):
+class ContinuityLossStandardized(_Continuity):
     """div U = 0 on standardised outputs (reference models/losses.py:167-190)."""
 
     def __init__(self, u_scaler: StandardScaler, points_scaler: StandardScaler):
@@ -138,7 +196,7 @@ class ContinuityLossStandardized(_ResidualSpec):
         self.u_scaler, self.points_scaler = u_scaler, points_scaler
 
 
-class MomentumLossManufactured(_ResidualSpec):
+class MomentumLossManufactured(_Momentum):
     """Raw-output momentum residual with forcing term (reference models/losses.py:193-225)."""
     kind = 'manufactured'
 
@@ -147,7 +205,7 @@ class MomentumLossManufactured(_ResidualSpec):
         self.nu, self.d, self.f = nu, d, f
 
 
-class MomentumLossFixed(_ResidualSpec):
+class MomentumLossFixed(_Momentum):
     """Standardised outputs, scalar Darcy / Forchheimer coefficients (reference models/losses.py:228-270)."""
     kind = 'fixed'
 
@@ -158,7 +216,7 @@ class MomentumLossFixed(_ResidualSpec):
         self.u_scaler, self.points_scaler, self.p_scaler = u_scaler, points_scaler, p_scaler
 
 
-class MomentumLossVariable(_ResidualSpec):
+class MomentumLossVariable(_Momentum):
     """Standardised outputs, per-point per-component coefficients (reference models/losses.py:273-319)."""
     kind = 'variable'
 

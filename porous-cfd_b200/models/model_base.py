@@ -63,9 +63,82 @@ class _StepGradients(torch.autograd.Function):
         return (None, None, *grads)
 
 
-def calculate_gradients(outputs, inputs):
-    raise NotImplementedError('reverse-mode sweeps are replaced by the forward-mode jet pass; use '
-                              'PorousPinnBase.jets(batch) to obtain U, jacobian, laplacian and grad p')
+class _JetVJPPoints(torch.autograd.Function):
+    """out[b,n,k] = sum_c g[b,n,c] * J1[b,n,c,k]: the reverse sweep `autograd.grad(y, points, g)` of a per-point model,
+    read off the forward-mode jet.  Differentiable once more for the Hessian DIAGONAL (what get_laplacian consumes): the
+    jet carries d2y_c/dx_k2 but no mixed partials, so entries of the second derivative that would need them are NaN
+    instead of silently wrong.  `points` is an input only so that autograd routes that second derivative to it."""
+
+    @staticmethod
+    def forward(ctx, points, g, j1, j2):
+        ctx.save_for_backward(g, j1, j2)
+        return torch.einsum('bnc,bnck->bnk', g, j1)
+
+    @staticmethod
+    def backward(ctx, gg):
+        g, j1, j2 = ctx.saved_tensors
+        grad_g = torch.einsum('bnk,bnck->bnc', gg, j1)
+        # d/dx_l of out = sum_c g_c sum_k gg_k d2y_c/(dx_k dx_l): the k == l term is known, any k != l with gg_k != 0
+        # would need a mixed partial
+        diag = torch.einsum('bnc,bnck->bnk', g, j2) * gg
+        nz = (gg != 0).to(diag.dtype)
+        mixed = nz.sum(-1, keepdim=True) - nz
+        diag = torch.where(mixed > 0, torch.full_like(diag, float('nan')), diag)
+        return diag, grad_g, None, None
+
+
+class _JetForward(torch.autograd.Function):
+    """Model.forward(autograd_points, x) as an autograd node over the points: forward runs ONE forward-mode jet pass
+    (values, d/dx_k, d2/dx_k2) through the CUDA kernels, backward answers `autograd.grad(y, points, g)` from the stored
+    jet instead of a reverse sweep through the network -- so the reference's helpers (calculate_gradients, get_jacobian,
+    get_laplacian, models/model_base.py:11-53) and its `predict_step` derivative stack work on this model unchanged.
+    Gradients with respect to the PARAMETERS do not flow through this node (training goes through training_step)."""
+
+    @staticmethod
+    def forward(ctx, points, model, x):
+        ex = model.executor
+        d = model.dims
+        b, n, _ = points.shape
+        yj = ex.forward_jets(points, x.data, x.labels, x.domain, order=2)
+        y = yj.t[:, :, :d + 1].reshape(1 + 2 * d, b, n, d + 1)
+        j1 = y[1:1 + d].permute(1, 2, 3, 0).contiguous()         # [b, n, c, k] = dy_c/dx_k
+        j2 = y[1 + d:1 + 2 * d].permute(1, 2, 3, 0).contiguous()  # [b, n, c, k] = d2y_c/dx_k2
+        ctx.save_for_backward(points, j1, j2)
+        return y[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        points, j1, j2 = ctx.saved_tensors
+        return _JetVJPPoints.apply(points, g, j1, j2), None, None
+
+
+def calculate_gradients(outputs: Tensor, inputs: Tensor) -> Tensor:
+    """d(sum of outputs)/d(inputs), differentiable again (reference models/model_base.py:11-20)."""
+    return torch.autograd.grad(outputs, inputs, grad_outputs=torch.ones_like(outputs), retain_graph=True,
+                               create_graph=True)[0]
+
+
+def get_jacobian(points: Tensor, u: Tensor) -> Tensor:
+    """jac[..., i, j] = dU_i/dx_j, one sweep per velocity component (reference models/model_base.py:23-35)."""
+    return torch.stack([calculate_gradients(u[..., i:i + 1], points) for i in range(points.shape[-1])], dim=-2)
+
+
+def get_laplacian(points: Tensor, jacobian: Tensor) -> Tensor:
+    """lap[..., i, j] = d/dx_j of jacobian[..., i, j] (reference models/model_base.py:38-53).  As in the reference,
+    passing U instead of the Jacobian (what training_step does at :195) slices the POINT axis and yields first
+    derivatives of the first D points."""
+    dims = points.shape[-1]
+    rows = []
+    for i in range(dims):
+        rows.append(torch.cat([calculate_gradients(jacobian[..., i:i + 1, j], points)[..., j:j + 1] for j in range(dims)], -1))
+    return torch.stack(rows, dim=-2)
+
+
+def enable_internal_autograd(batch: FoamData):
+    """(internal points as an autograd leaf, all points) (reference models/model_base.py:56-66)."""
+    internal_points = batch['internal']['C']
+    internal_points.requires_grad = True
+    return internal_points, torch.cat([internal_points, batch['boundary']['C']], dim=-2)
 
 
 class PorousPinnBase(_Base):
@@ -100,6 +173,7 @@ class PorousPinnBase(_Base):
         if self.loss_scaler is not None:
             self.loss_scaler = self.loss_scaler.to(*args, **kwargs)
         self._executor = None
+        self._prm_cache.clear()
         return self
 
     def get_predicted_labels(self) -> dict:
@@ -130,8 +204,24 @@ class PorousPinnBase(_Base):
         """{'kind', 'nu', 'd', 'f', scalers...} -- provided by the concrete model."""
         raise NotImplementedError
 
+    # attributes the residual parameters (and every captured step graph) are built from: assigning one of them drops the
+    # cached parameter blocks and the captured graphs.  In-place edits of a scaler's tensors are not seen -- call
+    # invalidate_residual_params() after such an edit.
+    _PRM_ATTRS = frozenset({'loss_scaler', 'enable_data_loss', 'u_scaler', 'p_scaler', 'points_scaler', 'd_scaler',
+                            'f_scaler', 'momentum_loss', 'continuity_loss', 'laplacian'})
+
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        if name in PorousPinnBase._PRM_ATTRS and '_prm_cache' in self.__dict__:
+            self.invalidate_residual_params()
+
+    def invalidate_residual_params(self) -> None:
+        self._prm_cache.clear()
+        if self.__dict__.get('_executor') is not None:
+            self._executor.reset_graphs()
+
     def residual_params(self, labels: dict, laplacian: str) -> ResidualParams:
-        key = (tuple(labels), laplacian)
+        key = (tuple(labels), laplacian, bool(self.enable_data_loss))
         if key in self._prm_cache:
             return self._prm_cache[key]
         spec = self.loss_spec()
@@ -167,7 +257,7 @@ class PorousPinnBase(_Base):
         if spec['kind'] in ('variable', 'manufactured'):
             prm.col_f[:d] = [col(n) for n in labels['f']]
         n_terms = 2 * d + 2 + ((d + 1) if self.enable_data_loss else 0)
-        w = self.loss_scaler.weights(n_terms) if self.loss_scaler is not None else [1.0] * n_terms
+        w = self.loss_scaler.weight_list(n_terms) if self.loss_scaler is not None else [1.0] * n_terms
         prm.weights[:] = (w + [0.0] * 16)[:16]
         self._prm_cache[key] = prm
         return prm
@@ -175,7 +265,11 @@ class PorousPinnBase(_Base):
     # ---- model API ----------------------------------------------------------------------------------
     def forward(self, autograd_points: Tensor, x: FoamData) -> FoamData:
         """Predictions at `autograd_points` (B, N, D): FoamData with columns [U..., p] and x's domain."""
-        y = self.executor.forward_values(autograd_points, x.data, x.labels, x.domain)
+        if autograd_points.requires_grad and torch.is_grad_enabled():
+            # derivative queries (get_jacobian / get_laplacian / calculate_gradients) are answered from the jet
+            y = _JetForward.apply(autograd_points, self, x)
+        else:
+            y = self.executor.forward_values(autograd_points, x.data, x.labels, x.domain)
         return FoamData(y, self.predicted_labels, x.domain)
 
     def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False, geo=None):

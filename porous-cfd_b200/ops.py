@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional
 
 import torch
@@ -148,6 +149,26 @@ def _weight_block(w: Tensor, col_lo: int, k: int, n: int):
     return buf.data_ptr(), buf.stride(0)
 
 
+# PCFD_ENGINE=0 (or ops.FORCE_FFMA = True) sends every jet layer to the generic fp32 CUDA-core engine under its own entry
+# points (pcfd_ffma_*): the independent implementation tests and scripts/bench_layers.py compare the tensor-core kernels
+# with.  The library itself has no engine switch.
+FORCE_FFMA = os.environ.get('PCFD_ENGINE', '2') == '0'
+# With AUDIT on, every jet layer call first asks pcfd_jet_linear_engine which kernel family will run it; layers of
+# tensor-core size that would fall to the generic FFMA engine are recorded in FALLBACKS (bench.py asserts it stays empty).
+AUDIT = False
+FALLBACKS: list = []
+
+
+def _audit(pass_id: int, a: 'Jet', w_ptr: int, ldw: int, b: 'Jet', tin, has_gescale: bool, k: int, n: int) -> None:
+    if not AUDIT or FORCE_FFMA:
+        return
+    eng = _lib.load().pcfd_jet_linear_engine(pass_id, a.t.data_ptr(), a.plane_stride, a.ld, w_ptr, ldw, b.t.data_ptr(),
+                                             b.plane_stride, b.ld, C.byref(tin) if tin is not None else None,
+                                             1 if has_gescale else 0, a.cj, a.rows, k, n)
+    if eng == _lib.ENGINE_FFMA and a.rows >= 512 and k >= 8 and n >= 16:      # 512 rows: the smallest dW the tensor-core kernel takes
+        FALLBACKS.append((('fwd', 'dx', 'dw')[pass_id], a.cj, a.rows, k, n))
+
+
 def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: int, bias: Optional[Tensor],
                    cvec: Optional[Tensor], rows_per_geom: int, n: int, out: Optional[Jet] = None) -> Jet:
     lib = _lib.load()
@@ -155,8 +176,10 @@ def jet_linear_fwd(zin: Jet, tin: Optional[InTrans], w: Tensor, col_lo: int, k: 
         out = Jet.empty(zin.cj, zin.rows, n, zin.t.device)
     _lib.launches += 1
     wptr, ldw = _weight_block(w, col_lo, k, n)
+    _audit(0, zin, wptr, ldw, out, tin, False, k, n)
+    fn = lib.pcfd_ffma_jet_linear_fwd if FORCE_FFMA else lib.pcfd_jet_linear_fwd
     with _timed(f'jet_fwd_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n, 4.0 * zin.cj * zin.rows * (k + n) + 4.0 * k * n):
-      check(lib.pcfd_jet_linear_fwd(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
+      check(fn(zin.t.data_ptr(), zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                   wptr, ldw, _ptr(bias), _ptr(cvec),
                                   cvec.stride(0) if cvec is not None else 0,
                                   out.t.data_ptr(), out.plane_stride, out.ld, zin.cj, zin.rows, rows_per_geom, k, n,
@@ -170,9 +193,11 @@ def jet_linear_bwd_dx(gzout: Jet, w: Tensor, col_lo: int, zin: Jet, tin: Optiona
     gzin = Jet.empty(zin.cj, zin.rows, k, zin.t.device)
     _lib.launches += 1
     wptr, ldw = _weight_block(w, col_lo, k, n)
+    _audit(1, gzout, wptr, ldw, zin, tin, gescale is not None, k, n)
+    fn = lib.pcfd_ffma_jet_linear_bwd_dx if FORCE_FFMA else lib.pcfd_jet_linear_bwd_dx
     with _timed(f'jet_dx_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n,
                 4.0 * zin.cj * zin.rows * (n + (2 * k if tin is not None else k)) + 4.0 * k * n):
-      check(lib.pcfd_jet_linear_bwd_dx(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, wptr,
+      check(fn(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, wptr,
                                      ldw, zin.t.data_ptr(), zin.plane_stride, zin.ld,
                                      C.byref(tin) if tin is not None else None,
                                      gzin.t.data_ptr(), gzin.plane_stride, gzin.ld, _ptr(gescale),
@@ -190,8 +215,11 @@ def jet_linear_bwd_dw(gzout: Jet, zin: Jet, tin: Optional[InTrans], gw: Optional
                       workspace: Tensor) -> None:
     lib = _lib.load()
     _lib.launches += 2 + (1 if (gbias is not None or gcvec is not None) else 0)
+    if gw is not None:
+        _audit(2, gzout, 0, 0, zin, tin, False, k, n)
+    fn = lib.pcfd_ffma_jet_linear_bwd_dw if FORCE_FFMA else lib.pcfd_jet_linear_bwd_dw
     with _timed(f'jet_dw_cj{zin.cj}', 2.0 * zin.cj * zin.rows * k * n, 4.0 * zin.cj * zin.rows * (k + n) + 4.0 * k * n):
-      check(lib.pcfd_jet_linear_bwd_dw(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
+      check(fn(gzout.t.data_ptr(), gzout.plane_stride, gzout.ld, zin.t.data_ptr(),
                                      zin.plane_stride, zin.ld, C.byref(tin) if tin is not None else None,
                                      (gw.data_ptr() + 4 * col_lo) if gw is not None else None,
                                      gw.stride(0) if gw is not None else 0, _ptr(gbias), _ptr(gcvec),
@@ -403,6 +431,47 @@ def residual_fields(data: Tensor, internal_ids: Tensor, y_int: Jet, prm: Residua
     return out
 
 
+def residual_eval(prm: ResidualParams, jac: Tensor, u: Optional[Tensor] = None, lap: Optional[Tensor] = None,
+                  p_grad: Optional[Tensor] = None, zone: Optional[Tensor] = None, dcoef: Optional[Tensor] = None,
+                  fcoef: Optional[Tensor] = None, want_momentum: bool = True, want_div: bool = False):
+    """Loss-module `func` on explicit tensors (pcfd_residual_eval): jac (..., D, D) [, u (..., D), lap (..., D, D),
+    p_grad (..., D), zone (..., 1), dcoef / fcoef (..., D)] -> (momentum (..., D) or None, div (...) or None)."""
+    lib = _lib.load()
+    d = prm.dims
+    lead = tuple(jac.shape[:-2])
+    rows = 1
+    for v in lead:
+        rows *= int(v)
+
+    def flat(t, w):
+        if t is None:
+            return None
+        t = _f32(t, 'residual_eval input').reshape(rows, w).contiguous()
+        return t
+
+    jac_f = flat(jac, d * d)
+    u_f, lap_f, pg_f = flat(u, d), flat(lap, d * d), flat(p_grad, d)
+    zone_f, dc_f, fc_f = flat(zone, 1), flat(dcoef, d), flat(fcoef, d)
+    mom = torch.empty((rows, d), dtype=torch.float32, device=jac.device) if want_momentum else None
+    div = torch.empty((rows,), dtype=torch.float32, device=jac.device) if want_div else None
+    _lib.launches += 1
+    check(lib.pcfd_residual_eval(_ptr(u_f), jac_f.data_ptr(), _ptr(lap_f), _ptr(pg_f), _ptr(zone_f), _ptr(dc_f), _ptr(fc_f),
+                                 rows, C.byref(prm), _ptr(mom), _ptr(div), _stream()), 'pcfd_residual_eval')
+    return (mom.reshape(*lead, d) if mom is not None else None, div.reshape(*lead) if div is not None else None)
+
+
+def mean_squares(x: Tensor) -> Tensor:
+    """(..., C) -> (C,) mean of squares over all leading dimensions; a 1-D / 0-D trailing shape counts as one column."""
+    lib = _lib.load()
+    x = _f32(x, 'mean_squares input')
+    cols = int(x.shape[-1]) if x.dim() >= 2 else 1
+    xf = x.reshape(-1, cols).contiguous()
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    _lib.launches += 1
+    check(lib.pcfd_mean_squares(xf.data_ptr(), xf.shape[0], cols, out.data_ptr(), _stream()), 'pcfd_mean_squares')
+    return out
+
+
 def relobralo_update(losses: Tensor, n: int, init_losses: Tensor, prev_losses: Tensor, lambda_ema: Tensor, step: Tensor,
                      batch_size: int, alpha: float, beta: float, tau: float, eps: float, seed: int,
                      weights_out: Tensor) -> None:
@@ -531,4 +600,9 @@ def copy_blocks_multi(srcs, dsts) -> None:
 
 
 def set_gemm_engine(engine: int) -> None:
-    check(_lib.load().pcfd_set_gemm_engine(engine), 'pcfd_set_gemm_engine')
+    """Host-side switch between the product path (2) and the generic fp32 CUDA-core engine (0) for every jet layer
+    issued from this process (tests / scripts/bench_layers.py).  The library has no such state."""
+    global FORCE_FFMA
+    if engine not in (0, 2):
+        raise _lib.PcfdError('jet GEMM engine must be 0 (fp32 FFMA reference engine) or 2 (tcgen05 product path)')
+    FORCE_FFMA = engine == 0

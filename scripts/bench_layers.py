@@ -47,7 +47,7 @@ OTHERS = [
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--engines', default='0,1,2')
+    ap.add_argument('--engines', default="0,2")
     ap.add_argument('--passes', default='fwd,dx,dw')
     ap.add_argument('--set', default='abc')
     ap.add_argument('--iters', type=int, default=20)

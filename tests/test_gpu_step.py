@@ -360,3 +360,158 @@ def test_steps_with_sparse_pool_backward_forced():
                             'test_step_matches_reference_fixture or test_full_width_models_match_oracle'],
                            env=env, capture_output=True, text=True, timeout=1500)
         assert r.returncode == 0, f'PCFD_POOL_SPARSE={mode}\n' + r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's Python seams on explicit tensors: calculate_gradients / get_jacobian / get_laplacian on the
+# output of Model.forward(autograd_points, x), and the loss modules' func / forward
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', PER_POINT)
+def test_derivative_helpers_on_forward_output(name):
+    """enable_internal_autograd -> forward -> get_jacobian / get_laplacian / calculate_gradients, written exactly as the
+    reference's training_step and predict_step write it (models/model_base.py:188-196, 236-240), against the oracle's
+    autograd sweeps: the documented Laplacian (Jacobian argument) and the as-written one (U argument)."""
+    from porous_cfd_b200.models.model_base import calculate_gradients, enable_internal_autograd, get_jacobian, get_laplacian
+    spec = synthetic.model_spec(name)
+    data, domain, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    batch = FoamData(data, labels, domain).to('cuda')
+    pts, all_points = enable_internal_autograd(batch)
+    predicted = model.forward(all_points, batch)
+    u_int = predicted['internal']['U']
+    jac = get_jacobian(pts, u_int)
+    lap_true = get_laplacian(pts, jac)
+    lap_ref = get_laplacian(pts, u_int)
+    d_p = calculate_gradients(predicted['internal']['p'], pts)
+    orc_t = pinn_oracle.training_step(spec, params, data, labels, domain, 'true')
+    orc_r = pinn_oracle.training_step(spec, params, data, labels, domain, 'reference')
+    assert rel_l2(predicted.data.detach().cpu().double(), orc_t['y'].detach().double()) < TOL
+    assert rel_l2(jac.detach().cpu().double(), orc_t['jac'].detach().double()) < TOL
+    assert rel_l2(d_p.detach().cpu().double(), orc_t['dp'].detach().double()) < TOL
+    assert rel_l2(lap_true.detach().cpu().double(), orc_t['lap'].detach().double()) < TOL
+    assert rel_l2(lap_ref.detach().cpu().double(), orc_r['lap'].detach().double()) < TOL
+    # the loss modules on those tensors (what the reference's predict_step does, models/model_base.py:241-246)
+    internal = batch['internal']
+    mom = model.momentum_loss.func(internal, u_int, jac, lap_true, d_p)
+    div = model.continuity_loss.func(jac)
+    d = spec['dims']
+    want = orc_t['residuals'].double()
+    assert rel_l2(mom.cpu().double(), want[..., :d]) < TOL
+    assert rel_l2(div.cpu().double(), want[..., d]) < TOL
+    m_loss = model.momentum_loss(internal, u_int, jac, lap_true, d_p)
+    c_loss = model.continuity_loss(jac)
+    assert tuple(m_loss.shape) == (d,) and c_loss.dim() == 0
+    assert max_rel(m_loss, (want[..., :d] ** 2).reshape(-1, d).mean(0)) < TOL
+    assert max_rel(c_loss, (want[..., d] ** 2).mean()) < TOL
+    # and they are the first terms of the fused step's unscaled loss vector
+    res = model.fused_step(batch, laplacian='true')
+    assert max_rel(res.unscaled[0], c_loss) < TOL and max_rel(res.unscaled[1:1 + d], m_loss) < TOL
+
+
+def test_mixed_second_derivatives_are_flagged_not_invented():
+    """The jet carries the Hessian diagonal only: a double derivative that needs mixed partials comes back NaN."""
+    from porous_cfd_b200.models.model_base import calculate_gradients, enable_internal_autograd
+    name = 'tiny_pigano'
+    spec = synthetic.model_spec(name)
+    data, domain, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    batch = FoamData(data, labels, domain).to('cuda')
+    pts, all_points = enable_internal_autograd(batch)
+    u = model.forward(all_points, batch)['internal']['U']
+    g = calculate_gradients(u[..., 0:1], pts)              # dU_0/dx
+    h = calculate_gradients(g[..., 0:1], pts)              # d/dx of dU_0/dx_0: [..., 0] known, [..., 1] mixed
+    assert bool(torch.isfinite(h[..., 0]).all()) and bool(torch.isnan(h[..., 1]).all())
+
+
+def test_residual_parameters_follow_attribute_changes():
+    """Replacing the loss scaler / switching the data loss off rebuilds the cached kernel parameters and drops the
+    captured graphs: the step reflects the new weights."""
+    from porous_cfd_b200.models.losses import FixedLossScaler
+    name = 'tiny_pigano'
+    spec = synthetic.model_spec(name)
+    data, domain, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    model = cuda_model(spec, params)
+    batch = FoamData(data, labels, domain).to('cuda')
+    base = model.fused_step(batch).out.clone()
+    n = int(base[37])
+    d = spec['dims']
+    w = {'continuity': [2.0], 'momentum': [3.0] * d, 'boundary': [5.0] * (d + 1), 'observations': [7.0] * (d + 1)}
+    model.loss_scaler = FixedLossScaler(w).to('cuda')
+    assert torch.is_tensor(model.loss_scaler.weights)        # the reference's attribute (models/losses.py:53)
+    out = model.fused_step(batch).out
+    want = base[:n] * model.loss_scaler.weights[:n]
+    assert max_rel(out[16:16 + n], want) < 1e-6
+    model.enable_data_loss = False
+    out2 = model.fused_step(batch)
+    assert out2.n_terms == 2 * d + 2
+
+
+# ---------------------------------------------------------------------------------------------
+# training mode: dropout inside the differentiated path (the benchmarked configuration)
+# ---------------------------------------------------------------------------------------------
+
+def _train_step_vs_oracle(spec, params, data, labels, domain, mode):
+    """One TRAINING-mode step (dropout on) against the oracle fed with the same masks (oracle/dropout_hash.py restates
+    the kernels' counter hash).  Returns (res, grads, oracle outputs)."""
+    from oracle.dropout_hash import CounterDropout
+    model = factory.build_model(spec)
+    model.load_state_dict(params, strict=True)
+    model = model.to('cuda').train()
+    batch = FoamData(data, labels, domain).to('cuda')
+    res = model.fused_step(batch, laplacian=mode)
+    torch.cuda.synchronize()
+    grads = {k: model.executor.ctx.grads[id(p)].clone() for k, p in model.named_parameters()}
+    seed = int(model.executor.ctx.seed_dev.item())            # the seed this step used (advanced at its start)
+    drop = CounterDropout(seed, domain['internal'].shape[1], domain['boundary'].shape[1])
+    orc = pinn_oracle.step_with_grads(spec, params, data, labels, domain, mode, training=True, dropout_fn=drop)
+    return res, grads, orc
+
+
+@pytest.mark.parametrize('name', ['tiny_pipn_pp', 'tiny_pigano', 'tiny_pigano_pp'])
+@pytest.mark.parametrize('mode', ['reference', 'true'])
+def test_training_mode_step_matches_oracle_with_the_same_masks(name, mode):
+    spec = synthetic.model_spec(name)
+    data, domain, params, out = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    res, grads, orc = _train_step_vs_oracle(spec, params, data, labels, domain, mode)
+    assert max_rel(res.losses, orc['losses']) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(orc['grads'], keys)) < TOL
+    # the masks did something: the eval-mode fixture differs
+    assert max_rel(res.losses, out[mode]['losses']) > 1e-3
+
+
+def test_full_shape_config2_training_step_matches_oracle():
+    """The benchmarked configuration itself: PIPN++ abc, 32 geometries x 1500 / 1000 / 700 points, dropout ON, every
+    loss term and the whole parameter gradient against the oracle (about 10 s of CPU autograd, once)."""
+    spec = synthetic.model_spec('abc_pipn_pp')
+    torch.manual_seed(3)
+    model = factory.build_model(spec)
+    params = synthetic.rescale_weights({k: v.detach().clone() for k, v in model.state_dict().items()}, 2.0)
+    data, labels, domain = synthetic.make_batch(spec['layout'], 32, 1500, 1000, 700, seed=8421)
+    res, grads, orc = _train_step_vs_oracle(spec, params, data, labels, domain, 'reference')
+    assert max_rel(res.losses, orc['losses']) < TOL
+    keys = list(params)
+    assert rel_l2(flat(grads, keys), flat(orc['grads'], keys)) < TOL
+
+
+def test_wide_layers_run_on_the_tensor_cores():
+    """No layer of tensor-core size silently falls to the generic FFMA engine in a full-width step (ops.AUDIT records
+    what pcfd_jet_linear_engine answers for every call)."""
+    from porous_cfd_b200 import ops
+    ops.AUDIT, ops.FALLBACKS[:] = True, []
+    try:
+        for name, shape in (('abc_pipn_pp', (8, 1500, 1000, 700)), ('duct_pigano', (4, 1500, 1000, 700))):
+            spec = synthetic.model_spec(name)
+            torch.manual_seed(3)
+            model = factory.build_model(spec).to('cuda').train()
+            data, labels, domain = synthetic.make_batch(spec['layout'], *shape, seed=1)
+            model.fused_step(FoamData(data, labels, domain).to('cuda'))
+            torch.cuda.synchronize()
+        assert ops.FALLBACKS == []
+    finally:
+        ops.AUDIT = False
