@@ -60,29 +60,46 @@ def mlp_chain(linears, act: str, last_activation: bool, dropout=None, first_act:
 
 
 class StepContext:
-    """Buffers shared by the calls of one executor: gradient views, scratch workspace, dropout seed."""
+    """Buffers shared by the calls of one executor: gradient views, scratch workspaces, dropout seed, streams."""
 
     def __init__(self, device):
         self.device = device
-        self.side_stream = None
-        # fork independent work to a side stream (off: one stream, for per-kernel timing / ordered ncu launch lists)
+        # fork independent work to side streams (off: one stream, for per-kernel timing / ordered ncu launch lists)
         self.overlap = os.environ.get('PCFD_NO_OVERLAP', '0') != '1'
-        self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=device)
+        # One scratch workspace PER STREAM (split partials of the dW kernels, residual partial sums): calls on one stream
+        # are ordered, so a stream's workspace can never be in use by two kernels at once, whatever runs beside it.
+        self.workspaces: dict = {}
         self.retired: list = []
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self.training = False
         self.grads: dict[int, Tensor] = {}
         self.salt = 0
         self.side_stream = None
+        self.streams: dict = {}
+        self.keep: list = []          # tensors produced on one stream and read on another: alive until the next step begins
 
-    def need_workspace(self, nbytes: int):
-        if self.workspace.numel() < nbytes:
-            if self.side_stream is not None:      # dW kernels on the side stream may still read the old buffer
-                self.side_stream.synchronize()
+    def stream(self, name: str) -> torch.cuda.Stream:
+        st = self.streams.get(name)
+        if st is None:
+            st = self.streams[name] = torch.cuda.Stream(device=self.device)
+        return st
+
+    def need_workspace(self, nbytes: int) -> Tensor:
+        """The current stream's workspace, at least `nbytes` large."""
+        key = torch.cuda.current_stream().cuda_stream
+        ws = self.workspaces.get(key)
+        if ws is None or ws.numel() < nbytes:
             # a captured step graph has the address of the workspace it was recorded with baked in: superseded buffers
             # stay allocated (they are a few MB) so that replaying an older graph never writes into freed memory
-            self.retired.append(self.workspace)
-            self.workspace = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            if ws is not None:
+                self.retired.append(ws)
+            ws = self.workspaces[key] = torch.empty(max(int(nbytes * 1.25) + 256, 1 << 20), dtype=torch.uint8, device=self.device)
+        return ws
+
+    @property
+    def workspace(self) -> Tensor:
+        """The current stream's workspace as sized by the last need_workspace() on this stream."""
+        return self.need_workspace(0)
 
     def grad(self, p: Optional[nn.Parameter]) -> Optional[Tensor]:
         return None if p is None else self.grads[id(p)]
@@ -112,25 +129,25 @@ def chain_backward(ctx: StepContext, layers, zs, gz: Jet, rows_per_geom: int, es
     """Reverse pass of a chain.  With `side`, the weight-gradient work of every layer (dW kernel + its small,
     latency-bound finish kernel) is issued on that stream while the main stream goes on with dX: the two big
     kernels still share the SMs one after the other, but the finish kernels no longer sit on the critical path.
-    The caller joins the streams (and owns the ordering of `ctx.workspace`, which the dW calls share)."""
+    The caller joins the streams; every stream has its own workspace (StepContext.need_workspace)."""
     main = torch.cuda.current_stream()
     for i in range(len(layers) - 1, -1, -1):
         L = layers[i]
         zin = zs[i]
         tin = _tin(ctx, L, escale, salt_base + i)
         nbytes = ops.dw_workspace_bytes(zin.cj, zin.rows, rows_per_geom, L.k, L.n)
-        ctx.need_workspace(nbytes)
         gbias = ctx.grad(L.bias) if L.cvec_key is None else None
         gcvec = gcvecs[L.cvec_key] if L.cvec_key is not None else None
         if side is not None:
             side.wait_stream(main)
             gz.t.record_stream(side)
+            ctx.keep += [gz, zin]
             with torch.cuda.stream(side):
                 ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
-                                      ctx.workspace)
+                                      ctx.need_workspace(nbytes))
         else:
             ops.jet_linear_bwd_dw(gz, zin, tin, ctx.grad(L.weight), L.col_lo, gbias, gcvec, rows_per_geom, L.k, L.n,
-                                  ctx.workspace)
+                                  ctx.need_workspace(nbytes))
         if i > 0 or need_input_grad:
             gz = ops.jet_linear_bwd_dx(gz, L.weight, L.col_lo, zin, tin, gescale if L.escale else None, rows_per_geom,
                                        L.k, L.n)
@@ -163,17 +180,18 @@ def pool_backward(ctx: StepContext, layers, zs, gout: Tensor, ldgout: int, arg: 
     worth = mode == '2' or k <= 16 or (seg_len >= 48 and n_seg >= 512)
     if mode != '0' and worth and plain and ops.pool_layer_bwd_supported(n_seg, seg_len, k, c, tin, zin.ld):
         need_gzin = len(layers) > 1 or need_input_grad
-        ctx.need_workspace(ops.pool_layer_bwd_workspace_bytes(n_seg, seg_len, k, c))
+        ws_bytes = ops.pool_layer_bwd_workspace_bytes(n_seg, seg_len, k, c)
         main = torch.cuda.current_stream()
         if side is not None:
             side.wait_stream(main)
             gout.record_stream(side)
+            ctx.keep.append(gout)
             with torch.cuda.stream(side):
                 ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
-                                   ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.workspace)
+                                   ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.need_workspace(ws_bytes))
         else:
             ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
-                               ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.workspace)
+                               ctx.grad(L.weight), ctx.grad(L.bias), False, ctx.need_workspace(ws_bytes))
         if not need_gzin:
             return None
         gzin = ops.pool_layer_bwd(gout, ldgout, arg, zsel, act_pool, n_seg, seg_len, c, zin, tin, k, L.weight,
@@ -447,9 +465,9 @@ class PinnExecutor:
         out, arg, zsel = ops.segmax_fwd_z(zs[-1].t[0], pending_act, None, n_seg, seg_len, c)
         return out, {'zs': zs, 'arg': arg, 'zsel': zsel, 'n_seg': n_seg, 'seg_len': seg_len, 'c': c, 'act': pending_act}
 
-    def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False):
+    def _segmax_features_bwd(self, ctx, layers, sv, gout: Tensor, ldgout: int, need_input_grad=False, side=None):
         return pool_backward(ctx, layers, sv['zs'], gout, ldgout, sv['arg'], sv['zsel'], sv['act'], sv['n_seg'], sv['seg_len'],
-                             rows_per_geom=sv['seg_len'], need_input_grad=need_input_grad, side=ctx.side_stream if ctx.overlap else None)
+                             rows_per_geom=sv['seg_len'], need_input_grad=need_input_grad, side=side)
 
     # ---- encode: per-geometry constants ------------------------------------------------------
     def _encode(self, data: Tensor, labels: dict, domain: dict, pts_int_ids, pts_bnd_ids, points: Optional[Tensor],
@@ -548,33 +566,112 @@ class PinnExecutor:
         gfeat, sv = self._segmax_features(ctx, plan['global_layers'], plan['global_pending_act'], gin, b, n_rows)
         return gfeat, plan['global_layers'][-1].n, {'zs_local': zs_local, 'global': sv, 'lw': lw}
 
-    def _encode_backward(self, saved: dict, gcvecs: dict, gescale: Optional[Tensor]):
+    def _encode_backward(self, saved: dict, gcvecs: dict, gescale: Optional[Tensor], dw_stream=None, gescale_ready=None):
+        """Reverse pass of the encoders on the current stream, their weight-gradient kernels on `dw_stream`.
+        `gescale_ready`: event after which `gescale` is complete (the branch part waits for it; the geometry part only
+        needs `gcvecs`, which the caller has ordered before this call)."""
         plan, ctx = self.plan, self.ctx
+        cur = torch.cuda.current_stream()
+        side = dw_stream
         cl = plan['concat_layer']
         gjet = saved['gjet']
         gcv = Jet(gcvecs['concat'].unsqueeze(0), cl.n)
-        ctx.need_workspace(ops.dw_workspace_bytes(1, gjet.rows, 0, cl.k, cl.n))
         ops.jet_linear_bwd_dw(gcv, gjet, None, ctx.grad(cl.weight), cl.col_lo, ctx.grad(cl.bias), None, 0, cl.k, cl.n,
-                              ctx.workspace)
+                              ctx.need_workspace(ops.dw_workspace_bytes(1, gjet.rows, 0, cl.k, cl.n)))
         gg = ops.jet_linear_bwd_dx(gcv, cl.weight, cl.col_lo, gjet, None, None, 0, cl.k, cl.n)
+        ctx.keep.append(gg)
         fam = plan['family']
         if fam in ('pipn_pp', 'pigano_pp'):
-            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld, side=ctx.side_stream if ctx.overlap else None)
+            sa_backward(ctx, plan['sa_stack'], saved['sa'], gg.t[0], gg.ld, side=side)
         elif fam == 'pigano':
-            self._segmax_features_bwd(ctx, plan['geom_layers'], saved['geom'], gg.t[0], gg.ld)
+            self._segmax_features_bwd(ctx, plan['geom_layers'], saved['geom'], gg.t[0], gg.ld, side=side)
         elif fam == 'pipn':
             sv = saved['pipn']
             gin = self._segmax_features_bwd(ctx, plan['global_layers'], sv['global'], gg.t[0], gg.ld,
-                                            need_input_grad=True)
+                                            need_input_grad=True, side=side)
             # gradient of the local features: first lw columns of the concat input, pending activation is
             # applied by the global MLP's first layer (act_cols = lw), so gin[:, :lw] is d/d z_local
             glocal = Jet(gin.t[:, :, :], sv['lw'])
-            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows,
-                           side=ctx.side_stream if ctx.overlap else None)
+            chain_backward(ctx, plan['local_layers'], sv['zs_local'], glocal, sv['zs_local'][0].rows, side=side)
         if fam in ('pigano', 'pigano_pp'):
-            self._segmax_features_bwd(ctx, plan['branch_layers'], saved['branch'], gescale, gescale.stride(0))
-        if ctx.side_stream is not None:
-            torch.cuda.current_stream().wait_stream(ctx.side_stream)
+            for ev in (gescale_ready or ()):
+                cur.wait_event(ev)
+            self._segmax_features_bwd(ctx, plan['branch_layers'], saved['branch'], gescale, gescale.stride(0), side=side)
+        if side is not None:
+            cur.wait_stream(side)
+
+    def _backward_overlapped(self, layers, zs_int, zs_bnd, gy_int: Jet, gy_bnd: Jet, ni: int, nb: int, escale, gescale,
+                             gcvecs: dict, saved: dict) -> None:
+        """Reverse pass as a dependency graph over five streams (fork / join on the current stream, so it is captured
+        into the step graph as parallel branches):
+
+            main    dX chain of the internal points (the large kernels)
+            bnd     dX chain of the boundary points (value only, small grids) -- independent of the internal chain
+            side    weight gradients of BOTH point chains, layer by layer in one stream order (they accumulate into the
+                    same gradient tensors); each waits only for the cotangent it consumes
+            enc     reverse pass of the encoders: starts as soon as the concat layer's per-geometry cotangent is complete
+                    (both chains' dW of that layer), i.e. while the point chains are still going back through the layers
+                    in front of it; the branch (PI-GANO) part waits for the last branch-scaled dX of both chains
+            encdw   the encoders' weight gradients
+
+        The encoder's reverse pass is a long chain of small, latency-bound launches (pooling, set-abstraction layers on a
+        few thousand rows) and the boundary chain runs one wave per kernel: next to the internal chain they cost nothing,
+        one after the other they were ~40 % of the backward (kernel timeline in profiles/r2_timeline_*.md)."""
+        ctx = self.ctx
+        main = torch.cuda.current_stream()
+        s_bnd, s_dw, s_enc, s_encdw = ctx.stream('bnd'), ctx.stream('side'), ctx.stream('enc'), ctx.stream('encdw')
+        for st in (s_bnd, s_dw, s_enc):
+            st.wait_stream(main)
+        ctx.keep += [gy_int, gy_bnd, gescale, gcvecs, zs_int, zs_bnd]
+        gz_i, gz_b = gy_int, gy_bnd
+        first_escale = min((i for i, L in enumerate(layers) if L.escale), default=None)
+        gescale_ready = None
+        for i in range(len(layers) - 1, -1, -1):
+            L = layers[i]
+            tin_i = _tin(ctx, L, escale, 100 + i)
+            tin_b = _tin(ctx, L, escale, 200 + i)
+            gbias = ctx.grad(L.bias) if L.cvec_key is None else None
+            gcvec = gcvecs[L.cvec_key] if L.cvec_key is not None else None
+            ev_i, ev_b = torch.cuda.Event(), torch.cuda.Event()
+            ev_i.record(main)
+            ev_b.record(s_bnd)
+            if L.cvec_key is not None:
+                # The encoders can go back as soon as the per-geometry cotangent of this layer's constant is known: it is
+                # the column sum of the value plane of gz per geometry, so it is formed here by the column-sum kernels
+                # alone (gw = None) instead of waiting for this layer's dW in the weight-gradient queue.
+                with torch.cuda.stream(s_enc):
+                    for ev, gz, zin, rpg in ((ev_i, gz_i, zs_int[i], ni), (ev_b, gz_b, zs_bnd[i], nb)):
+                        s_enc.wait_event(ev)
+                        g0, z0 = Jet(gz.t[0:1], gz.width), Jet(zin.t[0:1], zin.width)
+                        ops.jet_linear_bwd_dw(g0, z0, None, None, 0, None, gcvec, rpg, L.k, L.n,
+                                              ctx.need_workspace(ops.dw_workspace_bytes(1, gz.rows, rpg, L.k, L.n)))
+                    if first_escale is not None and gescale_ready is None:
+                        raise _lib.PcfdError('branch-scaled layers in front of the concat layer are not supported')
+                    self._encode_backward(saved, gcvecs, gescale, dw_stream=s_encdw, gescale_ready=gescale_ready)
+                gcvec = None
+            with torch.cuda.stream(s_dw):
+                s_dw.wait_event(ev_i)
+                zin = zs_int[i]
+                ops.jet_linear_bwd_dw(gz_i, zin, tin_i, ctx.grad(L.weight), L.col_lo, gbias, gcvec, ni, L.k, L.n,
+                                      ctx.need_workspace(ops.dw_workspace_bytes(zin.cj, zin.rows, ni, L.k, L.n)))
+                s_dw.wait_event(ev_b)
+                zin = zs_bnd[i]
+                ops.jet_linear_bwd_dw(gz_b, zin, tin_b, ctx.grad(L.weight), L.col_lo, gbias, gcvec, nb, L.k, L.n,
+                                      ctx.need_workspace(ops.dw_workspace_bytes(zin.cj, zin.rows, nb, L.k, L.n)))
+            if i > 0:
+                gz_i = ops.jet_linear_bwd_dx(gz_i, L.weight, L.col_lo, zs_int[i], tin_i, gescale if L.escale else None, ni,
+                                             L.k, L.n)
+                with torch.cuda.stream(s_bnd):
+                    gz_b = ops.jet_linear_bwd_dx(gz_b, L.weight, L.col_lo, zs_bnd[i], tin_b, gescale if L.escale else None,
+                                                 nb, L.k, L.n)
+                ctx.keep += [gz_i, gz_b]
+            if first_escale is not None and i == first_escale:
+                # gescale is complete once this layer's dX ran on both chains
+                gescale_ready = (torch.cuda.Event(), torch.cuda.Event())
+                gescale_ready[0].record(main)
+                gescale_ready[1].record(s_bnd)
+        for st in (s_bnd, s_dw, s_enc):
+            main.wait_stream(st)
 
     # ---- public entry points -----------------------------------------------------------------
     def forward_values(self, points: Tensor, data: Tensor, labels: dict, domain: dict) -> Tensor:
@@ -704,6 +801,7 @@ class PinnExecutor:
         c_cols = self._cols(labels, 'C')
 
         ops.begin_step()
+        ctx.keep.clear()
         ops.zero_(self.flat_grad)
         if ctx.training:
             ops.advance_seed(ctx.seed_dev)
@@ -714,8 +812,7 @@ class PinnExecutor:
         # side stream while the encoder occupies the main one (fork / join, also inside a captured graph).
         n_pre = next((i for i, L in enumerate(layers) if L.cvec_key is not None or L.escale), len(layers))
         main = torch.cuda.current_stream()
-        if ctx.side_stream is None:
-            ctx.side_stream = torch.cuda.Stream(device=data.device)
+        ctx.side_stream = ctx.stream('side')
         side = ctx.side_stream if ctx.overlap else main
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -763,17 +860,16 @@ class PinnExecutor:
         if escale is not None:
             gescale = torch.empty_like(escale)
             ops.zero_(gescale)
-        # the weight-gradient kernels of the two point chains go to the side stream (see chain_backward); the vanilla-PIPN
-        # coupling pass shares the workspace with them, so it keeps everything on one stream
-        wside = ctx.side_stream if (coup is None and ctx.overlap) else None
-        chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100, side=wside)
-        chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200, side=wside)
-        if wside is not None:
-            torch.cuda.current_stream().wait_stream(wside)
-        if coup is not None:
-            from . import coupling
-            coupling.backward(self, coup, data, int_ids, zs_int, gy_int, saved, gcvecs)
-        self._encode_backward(saved, gcvecs, gescale)
+        if coup is None and ctx.overlap:
+            self._backward_overlapped(layers, zs_int, zs_bnd, gy_int, gy_bnd, ni, nb, escale, gescale, gcvecs, saved)
+        else:
+            # one stream (per-kernel timing), or the vanilla-PIPN coupling pass whose reverse sweeps interleave with these
+            chain_backward(ctx, layers, zs_int, gy_int, ni, escale, gescale, gcvecs, salt_base=100)
+            chain_backward(ctx, layers, zs_bnd, gy_bnd, nb, escale, gescale, gcvecs, salt_base=200)
+            if coup is not None:
+                from . import coupling
+                coupling.backward(self, coup, data, int_ids, zs_int, gy_int, saved, gcvecs)
+            self._encode_backward(saved, gcvecs, gescale, dw_stream=ctx.stream('side') if ctx.overlap else None)
         ops.end_step()
 
         n_terms = 2 * d + 2 + ((d + 1) if obs_ids is not None else 0)
