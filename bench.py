@@ -10,7 +10,7 @@ through forward + NS-Darcy residual + backward), one process per GPU.
 A step = one pass of the hot path over one batch of synthetic geometries: zero gradients, encode
 (FPS / ball query / set abstraction), jet forward on internal + boundary points, fused residual,
 reverse pass to every parameter gradient, gradient all-reduce (N > 1) and the fused Adam update.
-Workload at every N: BASELINE config 2 -- PIPN++ (examples/abc, 3-D), 1500 / 1000 / 700 points,
+Headline workload at every N: BASELINE config 2 -- PIPN++ (examples/abc, 3-D), 1500 / 1000 / 700 points,
 32 geometries PER GPU (weak scaling), dropout on, laplacian='reference' (the operator the
 reference's training_step computes as written).
 
@@ -21,6 +21,9 @@ reference's training_step computes as written).
 `roofline`: the dominant kernel family of the step, timed per launch with CUDA events.
 `cpu_baseline`: the oracle (a port of the reference's algorithm: D + D*D + 1 reverse sweeps and a
            double backward in torch CPU) on a bounded sample of the same workload.
+`configs`: the other BASELINE.json configs at this N (config 3 and 5 strong-scaled: 64 / 256 geometries in total split
+           over the ranks; config 4 swept over geometries per GPU), device-resident, each with its dominant-family
+           roofline.  `--no-configs` skips them.
 """
 from __future__ import annotations
 
@@ -42,13 +45,11 @@ import pcfd_import  # noqa: E402
 pcfd_import.load()
 from porous_cfd_b200 import synthetic  # noqa: E402
 
-CONFIG = 'abc_pipn_pp'
-SHAPE = dict(n_internal=1500, n_boundary=1000, n_obs=700)
-B_PER_GPU = 32
 N_BATCHES = 4            # distinct synthetic batches cycled through
+METRIC = 'PINN train collocation points/sec (fwd+NS-Darcy residual+bwd)'
 
-# BASELINE.json configs 2-5 (config 2 is the default: the one the metric is quoted on for one GPU).  The others are
-# selectable with --config for DESIGN.md's per-config table; their parity is covered by tests/.
+# BASELINE.json configs 1-5 (config 2 is the headline: the one the metric is quoted on for one GPU).  The others are
+# selectable with --config and reported in the `configs` block of the default run; their parity is covered by tests/.
 WORKLOADS = {
     'abc_pipn': dict(shape=dict(n_internal=1500, n_boundary=1000, n_obs=700), batch=13,
                      what='PIPN abc 3-D, vanilla (examples/abc/train.py:26-34; max-pool coupling terms included)'),
@@ -102,25 +103,33 @@ class ClockSampler(threading.Thread):
                 'sm_max_mhz': int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, 'reasons': reasons}
 
 
-def make_model(device, train=True):
+def make_model(config: str, device, train=True):
     from porous_cfd_b200 import factory
-    spec = synthetic.model_spec(CONFIG)
+    spec = synthetic.model_spec(config)
     torch.manual_seed(3)
     model = factory.build_model(spec).to(device)
     return (model.train() if train else model.eval()), spec
 
 
-def cpu_reference_step_rate(steps: int, warmup: int, n_geom: int = 2):
-    """Times the oracle's training_step + backward (CPU, all host threads) on `n_geom` geometries of the
-    bench workload.  Returns (points/s, ms/step, threads)."""
+def shape_text(shape) -> str:
+    return f"{shape['n_internal']}/{shape['n_boundary']}/{shape['n_obs']}"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_step_rate(config: str, shape: dict, steps: int, warmup: int, n_geom: int):
+    """Times the oracle's training_step + backward (CPU, all host threads) on `n_geom` geometries of a workload.
+    Returns (points/s, ms/step, threads)."""
     from oracle import pinn_oracle
     from porous_cfd_b200 import factory
-    spec = synthetic.model_spec(CONFIG)
+    spec = synthetic.model_spec(config)
     torch.manual_seed(3)
     params = {k: v.detach().clone() for k, v in factory.build_model(spec).state_dict().items()}
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    data, labels, domain = synthetic.make_batch(spec['layout'], n_geom, seed=8421, **SHAPE)
+    data, labels, domain = synthetic.make_batch(spec['layout'], n_geom, seed=8421, **shape)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -128,26 +137,42 @@ def cpu_reference_step_rate(steps: int, warmup: int, n_geom: int = 2):
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
-    return n_geom * SHAPE['n_internal'] / (ms / 1e3), ms, threads
+    return n_geom * shape['n_internal'] / (ms / 1e3), ms, threads
 
 
-def run_reference(args):
+def run_reference(args, config: str, shape: dict, batch: int):
+    """--impl reference: the reference's CPU algorithm on the host cores, on THIS arm's config: every step processes all
+    `batch` geometries of one GPU's share of the workload (same config as the GPU arm; the step count is bounded because a
+    step takes seconds and is echoed in the line).  kind 'port': the reference itself needs lightning / torch_geometric /
+    torch_cluster, which this image does not have and which cannot travel to the GPU box; oracle/pinn_oracle.py is pinned
+    bit for bit on the unmodified reference by tests/golden/make_golden.py."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
-    n_geom = 2
-    pts, ms, threads = cpu_reference_step_rate(steps, warmup, n_geom)
-    line = {'impl': 'reference', 'metric': 'PINN train collocation points/sec (fwd+NS-Darcy residual+bwd)',
+    steps, warmup = max(1, min(args.steps, 3)), 1
+    pts, ms, threads = cpu_reference_step_rate(config, shape, steps, warmup, batch)
+    extra = []
+    if config == 'abc_pipn_pp' and not args.no_configs:
+        # BASELINE.md section 3: the reference's own CPU-runnable case (config 1, vanilla PIPN) at B = 1 and B = 13
+        for b, st in ((1, 3), (13, 2)):
+            p1, m1, _ = cpu_reference_step_rate('abc_pipn', WORKLOADS['abc_pipn']['shape'], st, 1, b)
+            extra.append({'config': 1, 'workload': f"abc_pipn: {WORKLOADS['abc_pipn']['what']}, "
+                                                   f"{shape_text(WORKLOADS['abc_pipn']['shape'])} points, {b} geometries per step",
+                          'value': p1, 'unit': 'points/s', 'ms_per_step': m1, 'steps': st, 'warmup': 1, 'cores': threads,
+                          'kind': 'port'})
+    line = {'impl': 'reference', 'metric': METRIC,
             'value': pts, 'unit': 'points/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms,
+            'steps_requested': args.steps, 'warmup_requested': args.warmup,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG}: {WORKLOADS[CONFIG]["what"]}, {SHAPE["n_internal"]}/{SHAPE["n_boundary"]}/'
-                                   f'{SHAPE["n_obs"]} points, CPU sample of {n_geom} geometries per step (bench workload: '
-                                   f'{B_PER_GPU} per GPU)', 'laplacian': 'reference'},
+            'config': {'workload': f'{config}: {WORKLOADS[config]["what"]}, {shape_text(shape)} points, '
+                                   f'{batch} geometries per GPU', 'global_batch': batch,
+                       'laplacian': 'reference', 'dropout': 'on',
+                       'note': 'one host, all cores: the CPU arm runs one GPU\'s share of the batch whatever --gpus says'},
             'cpu_baseline': {'value': pts, 'unit': 'points/s', 'cores': threads, 'kind': 'port',
-                             'sample': f'{n_geom} geometries x {SHAPE["n_internal"]} collocation points per step, {steps} steps'},
+                             'sample': f'{batch} geometries x {shape["n_internal"]} collocation points per step '
+                                       f'(the full per-GPU batch), {steps} timed steps after {warmup} warm-up'},
             'e2e': {'value': pts, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'gpu_launches': 0, 'configs': extra}
     _emit(line)
 
 
@@ -211,6 +236,375 @@ def ingest_leg(dev_batches, labels, n_internal, dims, peaks):
                     'bound': 'fp32 FMA (n x n_boundary distance evaluations per geometry)'}}
 
 
+# ------------------------------------------------------------------------------------------------
+# one workload on this rank's GPU
+# ------------------------------------------------------------------------------------------------
+
+class Env:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        self.device = torch.device('cuda', self.local)
+        torch.cuda.set_device(self.device)
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=self.device)
+        self.args = args
+        self.peaks = measured_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals
+        t = torch.tensor(list(vals), device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
+
+def family_roofline(fam: dict, prof_steps: int, peaks: dict, engine_name: str) -> dict:
+    """The `roofline` object of a workload from the per-family CUDA-event timings of the profiled leg."""
+    ms_prof = sum(v['ms'] for v in fam.values())
+    gemm = {k: v for k, v in fam.items() if k.startswith('jet_')}
+    top_name = max(gemm, key=lambda k: gemm[k]['ms'])
+    top = gemm[top_name]
+    # The jet layers of these workloads are narrow (k, n <= 512): their arithmetic intensity, k*n / (2*(k+n)) FLOP per
+    # byte = 27 for the widest layer of config 2, is below the 3xTF32 ridge of the B200 (~370 TFLOP/s effective /
+    # 6.5 TB/s = 57), so the bounding roofline of the dominant family is HBM bandwidth; the tensor-pipe figure is beside it.
+    achieved_gbs = top['bytes'] / (top['ms'] / 1e3) / 1e9
+    achieved_tf = top['work'] / (top['ms'] / 1e3) / 1e12
+    all_flops = sum(v['work'] for v in gemm.values())
+    all_bytes = sum(v['bytes'] for v in gemm.values())
+    all_ms = sum(v['ms'] for v in gemm.values())
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top_name)
+    roofline = {'bound': 'hbm', 'kernel': top_name, 'achieved': achieved_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved_gbs / peaks['hbm_gbs'], 'traffic': traffic,
+                'peak_source': peaks['source'] + ', copy bandwidth',
+                'algorithmic_bytes_per_launch': top['bytes'] / top['launches'],
+                'launches': top['launches'], 'avg_launch_ms': top['ms'] / top['launches'],
+                'share_of_step': top['ms'] / ms_prof, 'engine': engine_name,
+                'timing': 'CUDA events around every C-ABI call of an eagerly launched, single-stream step: includes the '
+                          'launch gaps of short kernels, so small families read low; the captured step is timed in `value`',
+                'tensor': {'achieved_tflops': achieved_tf, 'mma_tflops_3xtf32': 3 * achieved_tf,
+                           'peak_bf16_tflops': peaks['tflops_sustained'], 'frac_of_bf16_peak': 3 * achieved_tf / peaks['tflops_sustained']},
+                'all_jet_gemms': {'tflops': all_flops / (all_ms / 1e3) / 1e12,
+                                  'gbs': all_bytes / (all_ms / 1e3) / 1e9,
+                                  'hbm_frac': all_bytes / (all_ms / 1e3) / 1e9 / peaks['hbm_gbs'],
+                                  'share_of_step': all_ms / ms_prof},
+                'families_ms_per_step': {k: round(v['ms'] / prof_steps, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])},
+                'families_hbm_frac': {k: round(v['bytes'] / (v['ms'] / 1e3) / 1e9 / peaks['hbm_gbs'], 4) for k, v in gemm.items()}}
+    hbm = {}
+    for k in ('residual_loss', 'segmax_fwd', 'segmax_bwd', 'ball_query', 'sa_gather'):
+        if k in fam:
+            hbm[k] = {'gbs': fam[k]['work'] / (fam[k]['ms'] / 1e3) / 1e9, 'frac': fam[k]['work'] / (fam[k]['ms'] / 1e3) / 1e9 / peaks['hbm_gbs']}
+    roofline['hbm_kernels'] = hbm
+    if 'fps' in fam:
+        roofline['fps'] = {'ms_per_launch': fam['fps']['ms'] / fam['fps']['launches'], 'note': 'latency-bound (sequential sampling)'}
+    return roofline
+
+
+def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int, warmup: int, micro: int = 1,
+                 e2e: bool = True, seed_base: int = 0) -> dict:
+    """Times `steps` optimizer steps of one workload.  A step processes `b_per_gpu` geometries on every rank, as `micro`
+    micro-batches of b_per_gpu / micro geometries whose gradients accumulate (one all-reduce + one Adam update per step)."""
+    from porous_cfd_b200 import _lib, ops
+    from porous_cfd_b200.common.training import FlatAdamTrainer
+    from porous_cfd_b200.dataset.foam_data import FoamData
+    args, world, rank, device = env.args, env.world, env.rank, env.device
+    dist = env.dist
+    assert b_per_gpu % micro == 0
+    b_micro = b_per_gpu // micro
+    W, K = max(3, warmup), max(1, steps)
+    engine = 0 if ops.FORCE_FFMA else 2
+    engine_name = {0: 'fp32 FFMA (reference engine)', 2: 'TMA + tcgen05 3xTF32, warp-specialised'}[engine]
+    ops.AUDIT = True          # wide layers must run on the tensor cores: fallbacks are recorded and reported
+    ops.FALLBACKS.clear()
+
+    model, spec = make_model(config, device)
+    trainer = FlatAdamTrainer(model)
+    trainer.accumulate = micro
+    ex = model.executor
+    ni = shape['n_internal']
+
+    # distinct batches per rank, pinned on the host and resident on the device
+    host, dev_batches = [], []
+    n_batches = N_BATCHES if b_micro * (ni + shape['n_boundary']) < 4_000_000 else 2
+    for i in range(n_batches):
+        data, labels, domain = synthetic.make_batch(spec['layout'], b_micro, seed=seed_base + 1000 * rank + i, **shape)
+        hb = FoamData(data, labels, domain)
+        if e2e:
+            hb = hb.pin_memory()
+            host.append(hb)
+        dev_batches.append(hb.to(device))
+    h2d_bytes = dev_batches[0].data.numel() * 4 + sum(v.numel() * 8 for v in dev_batches[0].domain.values())
+
+    # ---- (1) device-resident throughput: CUDA graph of the whole step when possible ---------
+    static = FoamData(torch.empty_like(dev_batches[0].data), labels,
+                      {k: torch.empty_like(v) for k, v in dev_batches[0].domain.items()})
+    pipelined = (not args.no_pipeline) and (not args.no_graph) and ex.uses_geometry()
+    geo = None
+
+    def load_static(src: FoamData, dst: FoamData = static):
+        names = list(src.domain)      # the batch tensor and every sub-domain's ids in one launch
+        ops.copy_blocks_multi([src.data] + [src.domain[k] for k in names], [dst.data] + [dst.domain[k] for k in names])
+
+    def finish_step():
+        trainer.reduce_gradients()
+        trainer.step()
+
+    load_static(dev_batches[0])
+    l0 = _lib.launches
+    model.fused_step(static, args.laplacian)          # sizes the workspaces before any capture
+    launches_per_micro = _lib.launches - l0
+    finish_step()
+    torch.cuda.synchronize()
+    graph = None
+    tail_in_graph = False
+    if not args.no_graph:
+        # the optimizer tail (all-reduce at N > 1, Adam) is part of the graph when the step is one micro-batch; NCCL
+        # collectives are capturable, if this build refuses the graph is re-captured without the tail
+        for with_tail in ((True, False) if micro == 1 else (False,)):
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        model.fused_step(static, args.laplacian, accumulate=micro > 1)
+                        if micro == 1:
+                            finish_step()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                if pipelined:
+                    # geometry of the NEXT batch (positions only: FPS, ball query, edge slots) as an independent branch of
+                    # the graph; this batch's geometry sits in static buffers filled by the previous replay
+                    geo = ex.geometry(static.data, labels, static.domain)
+                    pos_next = ex.geometry_positions(dev_batches[1 % n_batches].data, labels, dev_batches[1 % n_batches].domain)
+                    geo_side = torch.cuda.Stream()
+                    torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    if pipelined:
+                        cap = torch.cuda.current_stream()
+                        geo_side.wait_stream(cap)
+                        with torch.cuda.stream(geo_side):
+                            geo_next = ex.geometry(None, labels, None, pos=pos_next)
+                    graph_res = model.fused_step(static, args.laplacian, geo=geo, accumulate=micro > 1)
+                    if with_tail:
+                        finish_step()      # all-reduce (N > 1) + fused Adam on the flat buffers, inside the graph
+                    if pipelined:
+                        cap.wait_stream(geo_side)
+                        for cur_l, new_l in zip(geo, geo_next):
+                            for gk in cur_l:
+                                cur_l[gk].copy_(new_l[gk])
+                tail_in_graph = with_tail
+                break
+            except Exception as e:  # report and fall back (still the CUDA path)
+                if rank == 0:
+                    print(f'[bench] CUDA graph capture failed (tail in graph: {with_tail}; {type(e).__name__}: {e})', file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
+
+    def micro_step(j):
+        if graph is not None:
+            load_static(dev_batches[j % n_batches])
+            if pipelined:      # the geometry branch reads only the sampled positions of the next batch: one gather launch
+                nb_ = dev_batches[(j + 1) % n_batches]
+                ex.geometry_positions(nb_.data, labels, nb_.domain, out=pos_next)
+            graph.replay()
+            return graph_res
+        return model.fused_step(dev_batches[j % n_batches], args.laplacian, accumulate=micro > 1)
+
+    def step(i):
+        if micro > 1:
+            ops.zero_(ex.flat_grad)
+        for m in range(micro):
+            res = micro_step(i * micro + m)
+        if not tail_in_graph:
+            finish_step()
+        return res
+
+    for i in range(W):
+        step(i)
+    env.barrier()
+    sampler = ClockSampler(env.local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        last = step(W + i)
+    e1.record()
+    env.barrier()
+    ms_total = e0.elapsed_time(e1)
+    loss_value = float(last.loss)
+
+    # ---- (2) end to end through the public API, host batches, loss read back ----------------
+    ms_e2e = None
+    if e2e:
+        params = list(model.parameters())
+        for p in params:
+            p.grad = None
+        # The call a user makes: model.training_step(batch) + loss.backward() + optimizer.step() (+ float(loss)), with
+        # model.cuda_graph = True (the fused step replays from a CUDA graph) and the NEXT step's pinned-host -> device
+        # copy issued on a copy stream while this step computes (every step still performs one full H2D copy of a batch
+        # inside the timed region, and reads its own loss back).
+        model.cuda_graph = True
+        copy_stream = torch.cuda.Stream()
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                b = model.transfer_batch_to_device(host[i % n_batches], device)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return b, ev
+
+        model.pipeline_geometry = pipelined
+        # with the geometry pipeline the graph of step i also reads the positions of batch i+1, so the copy of batch i+1
+        # was issued during step i-1 and this step issues the copy of batch i+2: still one batch copied per step
+        depth = 2 if pipelined else 1
+        pending = {'queue': [prefetch(j) for j in range(depth)]}
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        loss_ev = [None, None]
+
+        def read_loss(slot):
+            if loss_ev[slot] is None:
+                return None
+            loss_ev[slot].synchronize()
+            return float(loss_host[slot])
+
+        def e2e_step(i):
+            batch, ev = pending['queue'].pop(0)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            batch.data.record_stream(cur)
+            for v in batch.domain.values():
+                v.record_stream(cur)
+            if pipelined:
+                nxt, nev = pending['queue'][0]
+                cur.wait_event(nev)
+                nxt.data.record_stream(cur)
+                for v in nxt.domain.values():
+                    v.record_stream(cur)
+                model.announce_next_batch(nxt)
+            loss = model.training_step(batch, i)
+            pending['queue'].append(prefetch(i + depth))   # issued once this step's graph is enqueued: off the launch critical path
+            for p in params:
+                p.grad = None
+            loss.backward()
+            flat = model.executor.last_flat_grad      # every p.grad is a view of this buffer
+            trainer.reduce_gradients(flat)            # one NCCL all-reduce (N > 1); 1/world is folded into the Adam kernel
+            trainer.step(flat)                        # fused Adam on the flat parameter buffer (one launch)
+            if args.sync_loss:
+                return float(loss.detach())           # blocking device -> host read of the step's result
+            # device -> host read of EVERY step's loss through a pinned buffer; the host looks at it one step later (what a
+            # logging callback does), so the GPU already has the next step queued while the host waits for this one
+            slot = i & 1
+            loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ev[slot] = torch.cuda.Event()
+            loss_ev[slot].record()
+            return read_loss(slot ^ 1)
+
+        for i in range(W):
+            e2e_step(i)
+        env.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(K):
+            e2e_step(W + i)
+        if not args.sync_loss:
+            read_loss((W + K - 1) & 1)                # the last step's loss is read inside the timed region too
+        f1.record()
+        env.barrier()
+        ms_e2e = f0.elapsed_time(f1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- (3) per-kernel-family timing (eager, CUDA events around every C-ABI call) ------------
+    ops.PROFILE = ops.KernelProfile()
+    ex.ctx.overlap = False      # one stream: CUDA events around each call then time that call's kernels alone
+    prof_steps = min(K, 5) if micro == 1 else 1
+    for i in range(prof_steps):
+        model.fused_step(dev_batches[i % n_batches], args.laplacian)
+    fam = ops.PROFILE.summary()
+    ops.PROFILE = None
+    ex.ctx.overlap = True
+
+    ms_total, ms_e2e_m = env.max_over_ranks(ms_total, ms_e2e if ms_e2e is not None else 0.0)
+    pts_per_step = world * b_per_gpu * ni
+    out = {'value': pts_per_step * K / (ms_total / 1e3), 'ms_per_step': ms_total / K, 'steps': K, 'warmup': W,
+           'loss': loss_value, 'clocks': sampler.summary(), 'graph': graph is not None, 'tail_in_graph': tail_in_graph,
+           'pipelined': pipelined, 'h2d_bytes': h2d_bytes,
+           # kernels of this library per optimizer step: every micro-batch's fused step + its input copy (+ the position
+           # gather of the geometry branch), the gradient reset of an accumulated step, the two Adam launches
+           'launches_per_step': (launches_per_micro + 1 + (1 if pipelined else 0)) * micro + 2 + (1 if micro > 1 else 0),
+           'fallbacks': list(ops.FALLBACKS), 'b_micro': b_micro, 'micro': micro,
+           'roofline': family_roofline(fam, prof_steps, env.peaks, engine_name) if rank == 0 else None,
+           'dev_batches': dev_batches, 'labels': labels, 'spec': spec}
+    if e2e:
+        out['e2e_value'] = pts_per_step * K / (ms_e2e_m / 1e3)
+        out['e2e_ms_per_step'] = ms_e2e_m / K
+    return out
+
+
+def extra_configs(env: Env) -> list:
+    """The other BASELINE.json configs at this world size (see the module docstring).  Strong-scaled ones keep the total
+    number of geometries of the config and split it over the ranks; large per-rank batches run as micro-batches."""
+    world = env.world
+    plan = []
+    # config 3: PI-GANO duct_variable, batch 64 in total
+    plan.append(dict(config=3, name='duct_pigano', shape=WORKLOADS['duct_pigano']['shape'], total=64, micro_geoms=64,
+                     steps=20, scaling='strong'))
+    # config 4: PI-GANO++ windbreaks, geometries per GPU swept (weak)
+    for b in (1, 2, 4, 8):
+        plan.append(dict(config=4, name='windbreaks_pigano_pp', shape=WORKLOADS['windbreaks_pigano_pp']['shape'], per_gpu=b,
+                         micro_geoms=8, steps=10, scaling='weak'))
+    # config 5: manufactured PIPN++ sweep, 256 geometries in total; NB = NI / 4, no observations
+    for ni, mg, st in ((4096, 64, 10), (65536, 4, 3)) + (((262144, 1, 2),) if world >= 8 else ()):
+        plan.append(dict(config=5, name='manufactured_pipn_pp', shape=dict(n_internal=ni, n_boundary=ni // 4, n_obs=0),
+                         total=256, micro_geoms=mg, steps=st, scaling='strong'))
+    out = []
+    for p in plan:
+        if 'total' in p:
+            if p['total'] % world:
+                continue
+            b = p['total'] // world
+        else:
+            b = p['per_gpu']
+        b_micro = min(b, p['micro_geoms'])
+        while b % b_micro:
+            b_micro -= 1
+        micro = b // b_micro
+        r = None
+        try:
+            r = run_workload(env, p['name'], p['shape'], b, p['steps'], 3, micro=micro, e2e=False, seed_base=7000)
+            entry = {'config': p['config'], 'workload': f"{p['name']}: {WORKLOADS[p['name']]['what']}, {shape_text(p['shape'])} points, "
+                                                        f"{b} geometries per GPU x {world} GPU(s)",
+                     'global_batch': b * world, 'scaling': p['scaling'], 'value': r['value'], 'unit': 'points/s',
+                     'ms_per_step': r['ms_per_step'], 'steps': r['steps'], 'warmup': r['warmup'],
+                     'micro_batches_per_step': micro, 'cuda_graph': r['graph'], 'clocks': r['clocks'],
+                     'fallbacks': r['fallbacks']}
+            if r['roofline'] is not None:
+                rf = r['roofline']
+                entry['roofline'] = {k: rf[k] for k in ('bound', 'kernel', 'achieved', 'peak', 'unit', 'frac', 'share_of_step')}
+                entry['roofline']['all_jet_gemms'] = rf['all_jet_gemms']
+                entry['families_ms_per_step'] = rf['families_ms_per_step']
+        except Exception as e:       # an auxiliary measurement must not cost the bench line
+            entry = {'config': p['config'], 'workload': p['name'], 'error': f'{type(e).__name__}: {str(e)[:300]}'}
+            torch.cuda.synchronize()
+        out.append(entry)
+        del r
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -222,338 +616,80 @@ def main():
                     help='jet GEMM engine: 2 = warp-specialised TMA + tcgen05 (default), 0 = the generic fp32 FFMA reference engine')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the `configs` block (the other BASELINE configs)')
     ap.add_argument('--sync-loss', action='store_true', help='end-to-end leg: blocking float(loss) every step instead of the delayed read')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='compute the set-abstraction geometry (FPS, ball query) of a batch inside its own step instead of one step ahead')
     ap.add_argument('--laplacian', default='reference', choices=['reference', 'true'])
     ap.add_argument('--config', default='abc_pipn_pp', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='geometries per GPU (default: the config\'s own)')
+    ap.add_argument('--micro', type=int, default=1, help='micro-batches per optimizer step (gradient accumulation)')
     ap.add_argument('--n-internal', type=int, default=0,
                     help='collocation points per geometry (manufactured sweep: boundary = internal / 4)')
     args = ap.parse_args()
-    global CONFIG, SHAPE, B_PER_GPU
-    CONFIG = args.config
-    SHAPE = dict(WORKLOADS[CONFIG]['shape'])
-    B_PER_GPU = args.batch or WORKLOADS[CONFIG]['batch']
+    config = args.config
+    shape = dict(WORKLOADS[config]['shape'])
+    b_per_gpu = args.batch or WORKLOADS[config]['batch']
     if args.n_internal:
-        ratio = SHAPE['n_boundary'] / SHAPE['n_internal']
-        obs_ratio = SHAPE['n_obs'] / SHAPE['n_internal']
-        SHAPE = dict(n_internal=args.n_internal, n_boundary=int(args.n_internal * ratio), n_obs=int(args.n_internal * obs_ratio))
-    what = WORKLOADS[CONFIG]['what']
-    shape_txt = f"{SHAPE['n_internal']}/{SHAPE['n_boundary']}/{SHAPE['n_obs']}"
+        ratio = shape['n_boundary'] / shape['n_internal']
+        obs_ratio = shape['n_obs'] / shape['n_internal']
+        shape = dict(n_internal=args.n_internal, n_boundary=int(args.n_internal * ratio), n_obs=int(args.n_internal * obs_ratio))
+    what = WORKLOADS[config]['what']
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, config, shape, b_per_gpu)
 
-    import torch.distributed as dist
-    from porous_cfd_b200 import _lib, ops
-    from porous_cfd_b200.common.training import FlatAdamTrainer
-    from porous_cfd_b200.dataset.foam_data import FoamData
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    device = torch.device('cuda', local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
-    W, K = max(3, args.warmup), max(1, args.steps)
+    from porous_cfd_b200 import ops
+    env = Env(args)
     if args.engine is not None:
         ops.set_gemm_engine(args.engine)
-    engine = 0 if ops.FORCE_FFMA else 2
-    engine_name = {0: 'fp32 FFMA (reference engine)', 2: 'TMA + tcgen05 3xTF32, warp-specialised'}[engine]
-    ops.AUDIT = True          # wide layers must run on the tensor cores: fallbacks are recorded and reported
-
-    model, spec = make_model(device)
-    trainer = FlatAdamTrainer(model)
-    ex = model.executor
-    ni = SHAPE['n_internal']
-
-    # distinct batches per rank, pinned on the host and resident on the device
-    host, dev_batches = [], []
-    for i in range(N_BATCHES):
-        data, labels, domain = synthetic.make_batch(spec['layout'], B_PER_GPU, seed=1000 * rank + i, **SHAPE)
-        hb = FoamData(data, labels, domain).pin_memory()
-        host.append(hb)
-        dev_batches.append(hb.to(device))
-    h2d_bytes = host[0].data.numel() * 4 + sum(v.numel() * 8 for v in host[0].domain.values())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- (1) device-resident throughput: CUDA graph of the whole step when possible ---------
-    static = FoamData(torch.empty_like(dev_batches[0].data), labels,
-                      {k: torch.empty_like(v) for k, v in dev_batches[0].domain.items()})
-
-    pipelined = (not args.no_pipeline) and (not args.no_graph) and ex.uses_geometry()
-    geo = None
-
-    def load_static(src: FoamData, dst: FoamData = static):
-        names = list(src.domain)      # the batch tensor and every sub-domain's ids in one launch
-        ops.copy_blocks_multi([src.data] + [src.domain[k] for k in names], [dst.data] + [dst.domain[k] for k in names])
-
-    def eager_step(batch):
-        return trainer.train_step(batch, args.laplacian)
-
-    load_static(dev_batches[0])
-    l0 = _lib.launches
-    res = eager_step(static)          # sizes the workspace before any capture
-    launches_per_step = _lib.launches - l0
-    torch.cuda.synchronize()
-    use_graph = not args.no_graph
-    graph = None
-    if use_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    model.fused_step(static, args.laplacian)
-                    if world == 1:
-                        trainer.step()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            if pipelined:
-                # geometry of the NEXT batch (positions only: FPS, ball query, edge slots) as an independent branch of
-                # the graph; this batch's geometry sits in static buffers filled by the previous replay
-                geo = ex.geometry(static.data, labels, static.domain)
-                pos_next = ex.geometry_positions(dev_batches[1 % N_BATCHES].data, labels, dev_batches[1 % N_BATCHES].domain)
-                geo_side = torch.cuda.Stream()
-                torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                if pipelined:
-                    cap = torch.cuda.current_stream()
-                    geo_side.wait_stream(cap)
-                    with torch.cuda.stream(geo_side):
-                        geo_next = ex.geometry(None, labels, None, pos=pos_next)
-                graph_res = model.fused_step(static, args.laplacian, geo=geo)
-                if world == 1:
-                    trainer.step()      # fused Adam on the flat buffers, inside the graph (no collective at N = 1)
-                if pipelined:
-                    cap.wait_stream(geo_side)
-                    for cur_l, new_l in zip(geo, geo_next):
-                        for gk in cur_l:
-                            cur_l[gk].copy_(new_l[gk])
-        except Exception as e:  # report and fall back to per-kernel launches (still the CUDA path)
-            if rank == 0:
-                print(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); launching eagerly', file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
-
-    def step(i):
-        if graph is not None:
-            load_static(dev_batches[i % N_BATCHES])
-            if pipelined:      # the geometry branch reads only the sampled positions of the next batch: one gather launch
-                nb_ = dev_batches[(i + 1) % N_BATCHES]
-                ex.geometry_positions(nb_.data, labels, nb_.domain, out=pos_next)
-            graph.replay()
-            if world > 1:
-                trainer.reduce_gradients()
-                trainer.step()
-            return graph_res
-        return eager_step(dev_batches[i % N_BATCHES])
-
-    for i in range(W):
-        step(i)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        last = step(W + i)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    loss_value = float(last.loss)
-
-    # ---- (2) end to end through the public API, host batches, loss read back ----------------
-    params = list(model.parameters())
-    for p in params:
-        p.grad = None
-
-    # The call a user makes: model.training_step(batch) + loss.backward() + optimizer.step() (+ float(loss)), with
-    # model.cuda_graph = True (the fused step replays from a CUDA graph) and the NEXT step's pinned-host -> device
-    # copy issued on a copy stream while this step computes (every step still performs one full H2D copy of a batch
-    # inside the timed region, and reads its own loss back).
-    model.cuda_graph = True
-    copy_stream = torch.cuda.Stream()
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            b = model.transfer_batch_to_device(host[i % N_BATCHES], device)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return b, ev
-
-    model.pipeline_geometry = pipelined
-    # with the geometry pipeline the graph of step i also reads the positions of batch i+1, so the copy of batch i+1
-    # was issued during step i-1 and this step issues the copy of batch i+2: still one batch copied per step
-    depth = 2 if pipelined else 1
-    pending = {'queue': [prefetch(j) for j in range(depth)]}
-
-    def e2e_step(i):
-        batch, ev = pending['queue'].pop(0)
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev)
-        batch.data.record_stream(cur)
-        for v in batch.domain.values():
-            v.record_stream(cur)
-        if pipelined:
-            nxt, nev = pending['queue'][0]
-            cur.wait_event(nev)
-            nxt.data.record_stream(cur)
-            for v in nxt.domain.values():
-                v.record_stream(cur)
-            model.announce_next_batch(nxt)
-        loss = model.training_step(batch, i)
-        pending['queue'].append(prefetch(i + depth))   # issued once this step's graph is enqueued: off the launch critical path
-        for p in params:
-            p.grad = None
-        loss.backward()
-        flat = model.executor.last_flat_grad      # every p.grad is a view of this buffer
-        if world > 1:
-            dist.all_reduce(flat)                 # one NCCL all-reduce; 1/world is folded into the Adam kernel
-        trainer.step(flat)                        # fused Adam on the flat parameter buffer (one launch)
-        if args.sync_loss:
-            return float(loss.detach())           # blocking device -> host read of the step's result
-        # device -> host read of EVERY step's loss through a pinned buffer; the host looks at it one step later (what a
-        # logging callback does), so the GPU already has the next step queued while the host waits for this one
-        slot = i & 1
-        loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-        loss_ev[slot] = torch.cuda.Event()
-        loss_ev[slot].record()
-        return read_loss(slot ^ 1)
-
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    loss_ev = [None, None]
-
-    def read_loss(slot):
-        if loss_ev[slot] is None:
-            return None
-        loss_ev[slot].synchronize()
-        return float(loss_host[slot])
-
-    for i in range(W):
-        e2e_step(i)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for i in range(K):
-        e2e_step(W + i)
-    if not args.sync_loss:
-        read_loss((W + K - 1) & 1)                # the last step's loss is read inside the timed region too
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-
-    # ---- (3) per-kernel-family timing (eager, CUDA events around every C-ABI call) ------------
-    ops.PROFILE = ops.KernelProfile()
-    ex.ctx.overlap = False      # one stream: CUDA events around each call then time that call's kernels alone
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    prof_steps = min(K, 5)
-    for i in range(prof_steps):
-        model.fused_step(dev_batches[i % N_BATCHES], args.laplacian)
-    t1.record()
-    fam = ops.PROFILE.summary()
-    ops.PROFILE = None
-    ex.ctx.overlap = True
-    ms_prof = t0.elapsed_time(t1)
-
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+    r = run_workload(env, config, shape, b_per_gpu, args.steps, args.warmup, micro=args.micro, e2e=True)
+    headline_only = args.no_configs or config != 'abc_pipn_pp' or args.batch or args.n_internal or args.micro > 1
+    configs = None if headline_only else extra_configs(env)
+    if env.rank != 0:
+        if env.world > 1:
+            env.dist.destroy_process_group()
         return
 
-    pts_per_step = world * B_PER_GPU * ni
-    value = pts_per_step * K / (ms_total / 1e3)
-    e2e_value = pts_per_step * K / (ms_e2e / 1e3)
-    peaks = measured_peaks()
-    # shares are of the summed kernel time of a step (what the ncu launch list in profiles/ also reports): the profiled
-    # leg launches eagerly with an event pair around every call, so its wall time is not a step time
-    ms_prof = sum(v['ms'] for v in fam.values())
-    gemm = {k: v for k, v in fam.items() if k.startswith('jet_')}
-    top_name = max(gemm, key=lambda k: gemm[k]['ms'])
-    top = gemm[top_name]
-    # The jet layers of this workload are narrow (k, n <= 384): their arithmetic intensity, k*n / (2*(k+n)) FLOP per
-    # byte = 27 for the widest layer, is below the 3xTF32 ridge of the B200 (~370 TFLOP/s effective / 6.5 TB/s = 57),
-    # so the bounding roofline of the dominant family is HBM bandwidth; the tensor-pipe figure is reported beside it.
-    achieved_gbs = top['bytes'] / (top['ms'] / 1e3) / 1e9
-    achieved_tf = top['work'] / (top['ms'] / 1e3) / 1e12
-    all_gemm_flops = sum(v['work'] for v in gemm.values())
-    all_gemm_bytes = sum(v['bytes'] for v in gemm.values())
-    all_gemm_ms = sum(v['ms'] for v in gemm.values())
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top_name)
-    roofline = {'bound': 'hbm', 'kernel': top_name, 'achieved': achieved_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved_gbs / peaks['hbm_gbs'], 'traffic': traffic,
-                'peak_source': peaks['source'] + ', copy bandwidth',
-                'algorithmic_bytes_per_launch': top['bytes'] / top['launches'],
-                'launches': top['launches'], 'avg_launch_ms': top['ms'] / top['launches'],
-                'share_of_step': top['ms'] / ms_prof, 'engine': engine_name,
-                'tensor': {'achieved_tflops': achieved_tf, 'mma_tflops_3xtf32': 3 * achieved_tf,
-                           'peak_bf16_tflops': peaks['tflops_sustained'], 'frac_of_bf16_peak': 3 * achieved_tf / peaks['tflops_sustained']},
-                'all_jet_gemms': {'tflops': all_gemm_flops / (all_gemm_ms / 1e3) / 1e12,
-                                  'gbs': all_gemm_bytes / (all_gemm_ms / 1e3) / 1e9,
-                                  'hbm_frac': all_gemm_bytes / (all_gemm_ms / 1e3) / 1e9 / peaks['hbm_gbs'],
-                                  'share_of_step': all_gemm_ms / ms_prof},
-                'families_ms_per_step': {k: round(v['ms'] / prof_steps, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])},
-                'families_hbm_frac': {k: round(v['bytes'] / (v['ms'] / 1e3) / 1e9 / peaks['hbm_gbs'], 4) for k, v in gemm.items()}}
-    hbm = {}
-    for k in ('residual_loss', 'segmax_fwd', 'segmax_bwd', 'ball_query', 'sa_gather'):
-        if k in fam:
-            hbm[k] = {'gbs': fam[k]['work'] / (fam[k]['ms'] / 1e3) / 1e9, 'frac': fam[k]['work'] / (fam[k]['ms'] / 1e3) / 1e9 / peaks['hbm_gbs']}
-    roofline['hbm_kernels'] = hbm
-    if 'fps' in fam:
-        roofline['fps'] = {'ms_per_launch': fam['fps']['ms'] / fam['fps']['launches'], 'note': 'latency-bound (sequential sampling)'}
-
     ingest = None
-    if world == 1:
+    if env.world == 1:
         try:
-            ingest = ingest_leg(dev_batches, labels, SHAPE['n_internal'], spec['dims'], peaks)
+            ingest = ingest_leg(r['dev_batches'], r['labels'], shape['n_internal'], r['spec']['dims'], env.peaks)
         except Exception as e:      # an auxiliary measurement must not cost the bench line
             ingest = {'error': f'{type(e).__name__}: {e}'}
             torch.cuda.synchronize()
 
     cpu = None
     if not args.no_cpu_baseline:
-        pts, ms_cpu, threads = cpu_reference_step_rate(steps=6, warmup=2, n_geom=2)
+        pts, ms_cpu, threads = cpu_reference_step_rate(config, shape, steps=6, warmup=2, n_geom=2)
         cpu = {'value': pts, 'unit': 'points/s', 'cores': threads, 'kind': 'port', 'ms_per_step': ms_cpu,
-               'sample': f'2 of the {B_PER_GPU} geometries per step ({2 * ni} collocation points), 6 timed steps after 2 warm-up'}
+               'sample': f'2 of the {b_per_gpu} geometries per step ({2 * shape["n_internal"]} collocation points), 6 timed steps '
+                         f'after 2 warm-up (the whole batch on the CPU is what `--impl reference` times)'}
 
-    line = {'metric': 'PINN train collocation points/sec (fwd+NS-Darcy residual+bwd)', 'value': value, 'unit': 'points/s',
-            'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K, 'higher_is_better': True,
+    line = {'metric': METRIC, 'value': r['value'], 'unit': 'points/s',
+            'n_gpus': env.world, 'steps': r['steps'], 'warmup': r['warmup'], 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{CONFIG}: {what}, {shape_txt} points, '
-                                   f'{B_PER_GPU} geometries per GPU', 'global_batch': world * B_PER_GPU,
+            'config': {'workload': f'{config}: {what}, {shape_text(shape)} points, '
+                                   f'{b_per_gpu} geometries per GPU', 'global_batch': env.world * b_per_gpu,
                        'laplacian': args.laplacian, 'dropout': 'on', 'optimizer': 'fused Adam in the step',
-                       'parallelism': f'dp{world}', 'cuda_graph': graph is not None,
+                       'parallelism': f'dp{env.world}', 'cuda_graph': r['graph'],
+                       'collective': ('none (N = 1)' if env.world == 1 else
+                                      'one NCCL all-reduce of the flat gradient + Adam, ' +
+                                      ('captured in the step graph' if r['tail_in_graph'] else 'launched behind the step graph')),
+                       'micro_batches_per_step': r['micro'],
                        'geometry': ('FPS / ball query of batch t+1 run as a parallel branch of step t (positions only; '
-                                    'one batch worth per step)') if pipelined else 'inside the step',
+                                    'one batch worth per step)') if r['pipelined'] else 'inside the step',
                        'l2': 'per-step working set (jets + gradients ~1 GB) exceeds the 126 MB L2; 4 batches cycled, no flush'},
-            'loss': loss_value, 'clocks': sampler.summary(),
-            'e2e': {'value': e2e_value, 'unit': 'points/s', 'ms_per_step': ms_e2e / K, 'h2d_bytes_per_step': h2d_bytes,
+            'loss': r['loss'], 'clocks': r['clocks'],
+            'e2e': {'value': r['e2e_value'], 'unit': 'points/s', 'ms_per_step': r['e2e_ms_per_step'], 'h2d_bytes_per_step': r['h2d_bytes'],
                     'd2h_bytes_per_step': 4, 'api': 'model.cuda_graph = True; model.training_step(model.transfer_batch_to_device(host_batch)); loss.backward(); ' +
                            ('FlatAdamTrainer.step(); float(loss)  [next batch prefetched on a copy stream]' if args.sync_loss else
                             'FlatAdamTrainer.step(); loss copied to pinned host memory every step and read by the host one step later  '
                             '[next batches prefetched on a copy stream]')},
-            'gpu_launches': launches_per_step * K, 'roofline': roofline, 'cpu_baseline': cpu, 'ingest': ingest}
+            'gpu_launches': r['launches_per_step'] * r['steps'], 'tensor_core_fallbacks': r['fallbacks'],
+            'roofline': r['roofline'], 'cpu_baseline': cpu, 'ingest': ingest, 'configs': configs}
     _emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == '__main__':

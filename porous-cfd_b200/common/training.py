@@ -50,14 +50,22 @@ def build_arg_parser() -> ArgumentParser:
 
 
 class FlatAdamTrainer:
-    """Fused step + gradient all-reduce + fused Adam on flat buffers."""
+    """Fused step + gradient all-reduce + fused Adam on flat buffers.
+
+    Multi-GPU: ONE all-reduce of the flat fp32 gradient (3.4-6 MB), then the Adam kernel with the 1/world of DDP's
+    average folded in.  Both are graph-capturable (`dist.all_reduce` on NCCL is captured as a kernel node), so a
+    data-parallel step can replay as one graph: `reduce_gradients(); step()` inside the capture, as bench.py does.
+    Bucketing the reduction per chain was measured not to pay on this path: the tensor-core kernels of a step own the
+    whole GPU one after the other, the weight-gradient queue drains at the very end of the reverse pass, and the only
+    gradients that are final early (the last two decoder layers) are 6 % of the buffer."""
 
     def __init__(self, model, process_group=None):
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         ex = model.executor
-        # re-point every parameter into one flat buffer so that Adam is a single fused launch
+        # re-point every parameter into one flat buffer (same order as the executor's flat gradient) so that Adam is a
+        # single fused launch
         total = ex.flat_grad.numel()
         self.flat_param = torch.empty(total, dtype=torch.float32, device=ex.device)
         off = 0
@@ -78,10 +86,11 @@ class FlatAdamTrainer:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=ex.device)
         self.lr_dev = torch.full((1,), float(g['lr']), dtype=torch.float32, device=ex.device)
         self.optimizer = self     # `.optimizer.step()` of the earlier torch.optim-based trainer keeps working
+        self.accumulate = 1       # micro-batches per optimizer step (their gradients are summed; 1/accumulate in Adam)
 
-    def reduce_gradients(self):
+    def reduce_gradients(self, grad: Optional[torch.Tensor] = None):
         if self.world > 1:
-            dist.all_reduce(self.model.executor.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.model.executor.flat_grad if grad is None else grad, op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self, grad: Optional[torch.Tensor] = None):
         """Adam (torch.optim.Adam semantics) on the flat buffers, one kernel; 1/world of the all-reduce is folded in.
@@ -90,7 +99,7 @@ class FlatAdamTrainer:
         from .. import ops
         g = self.model.executor.flat_grad if grad is None else grad
         ops.adam_step(self.flat_param, g, self.exp_avg, self.exp_avg_sq, self.step_dev,
-                      self.lr_dev, self.betas[0], self.betas[1], self.eps, 1.0 / self.world)
+                      self.lr_dev, self.betas[0], self.betas[1], self.eps, 1.0 / (self.world * self.accumulate))
 
     def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
         res = self.model.fused_step(batch, laplacian)
@@ -102,9 +111,23 @@ class FlatAdamTrainer:
         """ExponentialLR, interval = epoch (reference models/pipn/pipn_foam.py:102-105)."""
         self.lr_dev.mul_(self.gamma)
 
+    # ---- trainer state (what Lightning's checkpoint carries beside the weights) ---------------------
+    def state_dict(self) -> dict:
+        return {'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(), 'step': self.step_dev.clone(),
+                'lr': self.lr_dev.clone(), 'dropout_seed': self.model.executor.ctx.seed_dev.clone()}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.exp_avg.copy_(state['exp_avg'])
+        self.exp_avg_sq.copy_(state['exp_avg_sq'])
+        self.step_dev.copy_(state['step'])
+        self.lr_dev.copy_(state['lr'])
+        if 'dropout_seed' in state:       # the counter behind the dropout masks: a resumed run draws the masks it would have
+            self.model.executor.ctx.seed_dev.copy_(state['dropout_seed'])
+
 
 def shard_batch(batch: FoamData, rank: int, world: int) -> FoamData:
-    """This rank's equal share of the geometries of a batch."""
+    """This rank's equal share of the geometries of an already collated batch (bench / tests; `train` shards the
+    dataset indices instead, see epoch_indices)."""
     b = batch.data.shape[0]
     if b % world != 0:
         raise ValueError(f'batch of {b} geometries does not split evenly over {world} ranks')
@@ -113,9 +136,43 @@ def shard_batch(batch: FoamData, rank: int, world: int) -> FoamData:
     return FoamData(batch.data[sl].contiguous(), batch.labels, {k: v[sl].contiguous() for k, v in batch.domain.items()})
 
 
+def epoch_indices(n: int, epoch: int, rank: int, world: int, shuffle: bool = True, seed: int = 8421) -> list:
+    """The sample indices rank `rank` visits in `epoch`: torch's DistributedSampler rule, which is what Lightning puts
+    behind the reference's DataLoader under DDP -- one permutation per epoch shared by all ranks (seed + epoch), padded
+    by wrap-around to a multiple of the world size, rank r takes every world-th index.  Every rank gets the same number
+    of samples, so no batch ever fails to split."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        idx = torch.randperm(n, generator=g).tolist()
+    else:
+        idx = list(range(n))
+    if world > 1:
+        total = (n + world - 1) // world * world
+        idx = (idx + idx[:total - n]) if total > n else idx
+        idx = idx[rank:total:world]
+    return idx
+
+
+class _EpochSampler(torch.utils.data.Sampler):
+    def __init__(self, n, rank, world, shuffle):
+        self.n, self.rank, self.world, self.shuffle, self.epoch = n, rank, world, shuffle, 0
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def __iter__(self):
+        return iter(epoch_indices(self.n, self.epoch, self.rank, self.world, self.shuffle))
+
+    def __len__(self):
+        return (self.n + self.world - 1) // self.world
+
+
 def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
     """Train `model`; writes model_meta.json and model.ckpt under logs_dir/lightning_logs/<name>
-    like the reference.  Under torchrun every rank takes its share of each batch."""
+    like the reference.  Under torchrun every rank draws `batch_size` geometries per step from its shard of the epoch
+    (DistributedSampler semantics: the global batch is world x batch_size, as with Lightning DDP).  `--checkpoint`
+    resumes weights, Adam moments / step / learning rate, epoch and global step (Lightning's `fit(ckpt_path=...)`)."""
     distributed = int(os.environ.get('WORLD_SIZE', '1')) > 1
     if distributed and not dist.is_initialized():
         dist.init_process_group('nccl')
@@ -125,12 +182,26 @@ def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
     torch.cuda.set_device(device)
     torch.manual_seed(8421)
 
-    train_loader = DataLoader(train_data, args.batch_size, True, num_workers=0, collate_fn=collate_fn, pin_memory=True)
-    val_loader = DataLoader(val_data, args.batch_size, False, num_workers=0, collate_fn=collate_fn, pin_memory=True)
+    workers = int(getattr(args, 'num_workers', 0))
+    sampler = _EpochSampler(len(train_data), rank, world, True)
+    train_loader = DataLoader(train_data, args.batch_size, sampler=sampler, num_workers=workers, collate_fn=collate_fn,
+                              pin_memory=True)
+    val_loader = DataLoader(val_data, args.batch_size, False, num_workers=workers, collate_fn=collate_fn, pin_memory=True)
     model = model.to(device).train()
+    scaler = getattr(model, 'loss_scaler', None)
+    if scaler is not None and hasattr(scaler, 'set_batch_size'):
+        scaler.set_batch_size(args.batch_size)      # the reference reads trainer.train_dataloader.batch_size
     trainer = FlatAdamTrainer(model)
+    start_epoch, global_step = 0, 0
     if args.checkpoint:
-        model.load_state_dict(torch.load(args.checkpoint, map_location=device)['state_dict'])
+        ckpt = torch.load(args.checkpoint, map_location=device)
+        model.load_state_dict(ckpt['state_dict'])
+        if 'trainer' in ckpt:
+            trainer.load_state_dict(ckpt['trainer'])
+        start_epoch = int(ckpt.get('epoch', 0))
+        global_step = int(ckpt.get('global_step', 0))
+        if scaler is not None and hasattr(scaler, 'set_global_step'):
+            scaler.set_global_step(global_step)
 
     log_dir = Path(args.logs_dir) / 'lightning_logs' / (args.name or 'version_0')
     if rank == 0:
@@ -139,21 +210,27 @@ def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
                 'N observations': args.n_observations, 'Precision': args.precision, 'Batch size': args.batch_size}
         (log_dir / 'model_meta.json').write_text(json.dumps(meta, indent=4))
 
+    def checkpoint(epoch_done: int) -> dict:
+        return {'state_dict': model.state_dict(), 'trainer': trainer.state_dict(), 'epoch': epoch_done,
+                'global_step': global_step}
+
     history = []
-    for epoch in range(args.epochs):
+    for epoch in range(start_epoch, args.epochs):
         model.train()
+        sampler.set_epoch(epoch)
+        res = None
         for batch in train_loader:
-            batch = shard_batch(batch, rank, world) if world > 1 else batch
             res = trainer.train_step(model.transfer_batch_to_device(batch, device))
+            global_step += 1
         trainer.end_epoch()
-        if rank == 0:
+        if rank == 0 and res is not None:
             history.append(float(res.loss))
         if val_loader is not None and len(val_data) > 0:
             model.eval()
             for batch in val_loader:
                 model.validation_step(model.transfer_batch_to_device(batch, device))
         if rank == 0 and (epoch + 1) % 500 == 0:
-            torch.save({'state_dict': model.state_dict(), 'epoch': epoch}, log_dir / f'checkpoint-{epoch}.ckpt')
+            torch.save(checkpoint(epoch + 1), log_dir / f'checkpoint-{epoch}.ckpt')
     if rank == 0:
-        torch.save({'state_dict': model.state_dict(), 'epoch': args.epochs}, log_dir / 'model.ckpt')
+        torch.save(checkpoint(args.epochs), log_dir / 'model.ckpt')
     return history

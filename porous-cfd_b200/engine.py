@@ -783,8 +783,9 @@ class PinnExecutor:
         return sa_geometry(self.plan['sa_stack'], pos)
 
     def step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
-             keep_outputs: bool = False, geo: Optional[list] = None) -> StepResult:
-        """One fused training step: fills the flat gradient buffer and returns the loss vector."""
+             keep_outputs: bool = False, geo: Optional[list] = None, accumulate: bool = False) -> StepResult:
+        """One fused training step: fills the flat gradient buffer and returns the loss vector.  `accumulate`: add to
+        the gradient buffer instead of overwriting it (micro-batches of one optimizer step)."""
         plan, ctx = self.plan, self.ctx
         model = self.model
         ctx.training = model.training
@@ -802,7 +803,8 @@ class PinnExecutor:
 
         ops.begin_step()
         ctx.keep.clear()
-        ops.zero_(self.flat_grad)
+        if not accumulate:
+            ops.zero_(self.flat_grad)
         if ctx.training:
             ops.advance_seed(ctx.seed_dev)
 

@@ -73,16 +73,33 @@ class RelobraloScaler(LossScaler):
         self.seed = 8421
         self._step = None       # device int64 counter
         self._weights = None    # device float32[16]
+        self._resume_step = 0   # value the counter starts from when it is (re)created: > 0 after a state was loaded
 
     def set_batch_size(self, batch_size: int) -> None:
         self.batch_size = int(batch_size)
+
+    def set_global_step(self, step: int) -> None:
+        """The reference keys its update on `model.global_step`, which Lightning restores from the checkpoint; here the
+        counter lives on the device, so a resumed run hands it over explicitly (common.training.train does)."""
+        self._resume_step = int(step)
+        if self._step is not None:
+            self._step.fill_(int(step))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        # Buffers restored from a checkpoint belong to a run that is past its first step: the kernel's step-0 branch
+        # would overwrite init_losses / prev_losses with the current losses.  Without an explicit global step the
+        # counter restarts at 1 (any positive value keeps the restored statistics).
+        key = prefix + 'init_losses'
+        if key in state_dict and bool((state_dict[key] != 0).any()):
+            self.set_global_step(max(1, self._resume_step))
 
     def weight_list(self, n_terms: int) -> list[float]:
         return [1.0] * n_terms     # the static slot of the residual parameters; the live weights are on the device
 
     def device_state(self, device):
         if self._step is None or self._step.device != device:
-            self._step = torch.zeros(1, dtype=torch.int64, device=device)
+            self._step = torch.full((1,), self._resume_step, dtype=torch.int64, device=device)
             self._weights = torch.ones(16, dtype=torch.float32, device=device)
         return self._step, self._weights
 

@@ -272,10 +272,13 @@ class PorousPinnBase(_Base):
             y = self.executor.forward_values(autograd_points, x.data, x.labels, x.domain)
         return FoamData(y, self.predicted_labels, x.domain)
 
-    def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False, geo=None):
+    def fused_step(self, batch: FoamData, laplacian: Optional[str] = None, keep_outputs: bool = False, geo=None,
+                   accumulate: bool = False):
         """The hot path without the autograd wrapper: fills `executor.flat_grad`, returns StepResult.  `geo`: the
-        batch's set-abstraction geometry when it was computed ahead (`executor.geometry`)."""
-        return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs, geo)
+        batch's set-abstraction geometry when it was computed ahead (`executor.geometry`); `accumulate`: add this
+        batch's gradient to the buffer (micro-batches of one optimizer step)."""
+        return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs, geo,
+                                  accumulate)
 
     def announce_next_batch(self, batch: Optional[FoamData]) -> None:
         """Optional hint for `pipeline_geometry`: the batch the NEXT training_step call will receive (already on the
