@@ -313,6 +313,23 @@ int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n_rows, int3
                          float* gy_int, float* gy_bnd, float* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* The residual stage of a training step in ONE kernel launch (north-star (c): continuity, momentum with the
+ * Darcy-Forchheimer terms, boundary and observation MSE, weighting, reduction and d loss / d jet): same arguments and
+ * results as pcfd_residual_loss_w.  Blocks take the internal, boundary and observation points by role; the block that
+ * finishes last reduces the per-block partial sums in a fixed order.  The value plane of gy is accumulated with
+ * atomics, so it is zeroed first by one cudaMemsetAsync on `stream` (one memset node when gy_int directly follows
+ * gy_bnd in memory).  `ticket`: a device int32 that is zero before the first call and is left at zero by every call;
+ * the caller owns it and must not share it between streams.  Replaces the same reference code as pcfd_residual_loss
+ * (models/losses.py:149-319, models/model_base.py:191-218). */
+int pcfd_residual_step(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                       const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                       const int64_t* obs_ids, int64_t no,
+                       const float* y_int, int64_t y_plane_stride, const float* y_bnd, int32_t ldy,
+                       const pcfd_residual_params_t* prm_host, const float* weights_dev,
+                       const float* visc_extra, float* gvisc,
+                       float* gy_int, float* gy_bnd, float* out, int32_t* ticket,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Residual fields at inference, predict_step with verbose_predict (models/model_base.py:233-252):
  * fields [n_geom*ni][D+1] = cat([momentum residual (D), divergence]) at the internal points. */
 int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,

@@ -85,6 +85,8 @@ SIGNATURES = {
                                      C.POINTER(ResidualParams), _P, _P, _P, _P, _SZ, _P]),
     'pcfd_residual_loss_w': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
                                        C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'pcfd_residual_step': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32,
+                                     C.POINTER(ResidualParams), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
     'pcfd_residual_eval': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(ResidualParams), _P, _P, _P]),
     'pcfd_mean_squares': (C.c_int, [_P, _I64, _I32, _P, _P]),

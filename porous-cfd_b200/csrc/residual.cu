@@ -27,11 +27,13 @@ struct ResArgs {
   float* fields;                      // optional per-point residual map [n_geom*ni][D+1] = (momentum xD, div)
   const float* visc_extra;            // optional [n_geom*ni][D]: added to the Laplacian row sums (vanilla-PIPN coupling)
   float* gvisc;                       // optional [n_geom*ni][D]: d loss / d visc_extra
+  int vec_rows;                       // jet rows are 16-byte aligned and 4 floats apart or more: float4 loads / stores
 };
 
 #define PCFD_WT(i) (a.wdev != nullptr ? __ldg(a.wdev + (i)) : P.weights[i])
 
-__device__ __forceinline__ void block_reduce_store(float (&v)[NSLOT], float* partial) {
+// sums of the block -> dst[0..NSLOT)
+__device__ __forceinline__ void block_reduce_store(float (&v)[NSLOT], float* dst) {
   __shared__ float red[8][NSLOT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -45,19 +47,41 @@ __device__ __forceinline__ void block_reduce_store(float (&v)[NSLOT], float* par
   if (threadIdx.x < NSLOT) {
     float t = 0.0f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
-    partial[(int64_t)blockIdx.x * NSLOT + threadIdx.x] = t;
+    dst[threadIdx.x] = t;
+  }
+}
+
+// one output-jet row (D + 1 values, ld floats apart rows): a single 16-byte load / store when the layout allows
+template <int D>
+__device__ __forceinline__ void load_row(const float* p, bool vec, float (&v)[D + 1]) {
+  if (vec) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z;
+    if (D == 3) v[D] = q.w;
+  } else {
+#pragma unroll
+    for (int o = 0; o <= D; ++o) v[o] = __ldg(p + o);
+  }
+}
+template <int D>
+__device__ __forceinline__ void store_row(float* p, bool vec, const float (&v)[D + 1]) {
+  if (vec) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], D == 3 ? v[D] : 0.0f);
+  } else {
+#pragma unroll
+    for (int o = 0; o <= D; ++o) p[o] = v[o];
   }
 }
 
 // slots: [0] continuity, [1..D] momentum, [D+1..2D] |U error|, [2D+1] |p error|
-template <int D, int LAP>
-__global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
+// ATOMIC0: the value plane of gy is accumulated with atomics onto a zeroed buffer (the fused step kernel, where the
+// observation blocks add to the same entries in no particular order); otherwise plain stores.
+template <int D, int LAP, bool ATOMIC0>
+__device__ __forceinline__ void internal_body(const ResArgs& a, int64_t blk, float (&sums)[NSLOT]) {
   constexpr int CJ = LAP == PCFD_LAP_TRUE ? 1 + 2 * D : 1 + D;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = blk * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)a.n_geom * a.ni;
-  float sums[NSLOT];
-#pragma unroll
-  for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
+  const bool vec = a.vec_rows != 0;
   if (t < total) {
     const pcfd_residual_params_t& P = a.p;
     const int64_t g = t / a.ni, i = t % a.ni;
@@ -65,9 +89,7 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
     const float* erow = a.data + (g * a.n_rows + i) * a.f;                   // calculate_errors pairs row i with row i
     float y[CJ][D + 1];
 #pragma unroll
-    for (int c = 0; c < CJ; ++c)
-#pragma unroll
-      for (int o = 0; o <= D; ++o) y[c][o] = __ldg(a.y_int + c * a.ps + t * a.ldy + o);
+    for (int c = 0; c < CJ; ++c) load_row<D>(a.y_int + c * a.ps + t * a.ldy, vec, y[c]);
 
     const bool manu = P.loss_kind == PCFD_LOSS_MANUFACTURED;
     float su[D], mu[D], sx[D], dcoef[D], fcoef[D];
@@ -179,23 +201,32 @@ __global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
 #pragma unroll
     for (int d = 0; d < D; ++d) gy[0][d] += gur[d] * su[d];
     if (a.gy_int != nullptr) {
+      if (ATOMIC0) {
 #pragma unroll
-      for (int c = 0; c < CJ; ++c)
+        for (int o = 0; o <= D; ++o) atomicAdd(a.gy_int + t * a.ldy + o, gy[0][o]);
+      } else {
+        store_row<D>(a.gy_int + t * a.ldy, vec, gy[0]);
+      }
 #pragma unroll
-        for (int o = 0; o <= D; ++o) a.gy_int[c * a.ps + t * a.ldy + o] = gy[c][o];
+      for (int c = 1; c < CJ; ++c) store_row<D>(a.gy_int + c * a.ps + t * a.ldy, vec, gy[c]);
     }
   }
-  if (a.partial != nullptr) block_reduce_store(sums, a.partial);
 }
 
-// slots: [0..D-1] (U - target)^2, [D] (p - target)^2, [D+1..2D] |U error|, [2D+1] |p error|
-template <int D>
-__global__ void __launch_bounds__(256) residual_boundary_kernel(ResArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)a.n_geom * a.nb;
+template <int D, int LAP>
+__global__ void __launch_bounds__(256) residual_internal_kernel(ResArgs a) {
   float sums[NSLOT];
 #pragma unroll
   for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
+  internal_body<D, LAP, false>(a, blockIdx.x, sums);
+  if (a.partial != nullptr) block_reduce_store(sums, a.partial + (int64_t)blockIdx.x * NSLOT);
+}
+
+// slots: [0..D-1] (U - target)^2, [D] (p - target)^2, [D+1..2D] |U error|, [2D+1] |p error|
+template <int D, bool ATOMIC0>
+__device__ __forceinline__ void boundary_body(const ResArgs& a, int64_t blk, float (&sums)[NSLOT]) {
+  const int64_t t = blk * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)a.n_geom * a.nb;
   if (t < total) {
     const pcfd_residual_params_t& P = a.p;
     const int64_t g = t / a.nb, j = t % a.nb;
@@ -209,22 +240,28 @@ __global__ void __launch_bounds__(256) residual_boundary_kernel(ResArgs a) {
       const float diff = yv - __ldg(drow + col);
       sums[o] = diff * diff;
       const float w = PCFD_WT(1 + D + o);
-      a.gy_bnd[t * a.ldy + o] = 2.0f * w * diff * a.inv_bnd;
+      if (ATOMIC0) atomicAdd(a.gy_bnd + t * a.ldy + o, 2.0f * w * diff * a.inv_bnd);
+      else a.gy_bnd[t * a.ldy + o] = 2.0f * w * diff * a.inv_bnd;
       const float sc = manu ? 1.0f : (o < D ? P.u_std[o] : P.p_std);
       sums[D + 1 + o] = fabsf(sc * (yv - __ldg(erow + col)));
     }
   }
-  block_reduce_store(sums, a.partial);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) residual_boundary_kernel(ResArgs a) {
+  float sums[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
+  boundary_body<D, false>(a, blockIdx.x, sums);
+  block_reduce_store(sums, a.partial + (int64_t)blockIdx.x * NSLOT);
 }
 
 // slots: [0..D-1] obs U, [D] obs p.  Adds its gradient on top of what the two kernels above wrote.
 template <int D>
-__global__ void __launch_bounds__(256) residual_obs_kernel(ResArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void obs_body(const ResArgs& a, int64_t blk, float (&sums)[NSLOT]) {
+  const int64_t t = blk * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)a.n_geom * a.no;
-  float sums[NSLOT];
-#pragma unroll
-  for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
   if (t < total) {
     const pcfd_residual_params_t& P = a.p;
     const int64_t g = t / a.no;
@@ -241,7 +278,15 @@ __global__ void __launch_bounds__(256) residual_obs_kernel(ResArgs a) {
       atomicAdd(grow + o, 2.0f * PCFD_WT(2 + 2 * D + o) * diff * a.inv_obs);
     }
   }
-  block_reduce_store(sums, a.partial);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) residual_obs_kernel(ResArgs a) {
+  float sums[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
+  obs_body<D>(a, blockIdx.x, sums);
+  block_reduce_store(sums, a.partial + (int64_t)blockIdx.x * NSLOT);
 }
 
 struct FinishArgs {
@@ -249,7 +294,7 @@ struct FinishArgs {
   int dims, data_loss; float inv_int, inv_bnd, inv_obs, inv_all; float weights[16]; const float* wdev; float* out;
 };
 
-__global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
+__device__ __forceinline__ void finish_body(const FinishArgs& a) {
   __shared__ double tot[3 * NSLOT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // one warp per (region, slot) sum, three rounds of eight: fixed order -> deterministic
@@ -258,7 +303,7 @@ __global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
     const float* p = region == 0 ? a.p_int : (region == 1 ? a.p_bnd : a.p_obs);
     const int nb = region == 0 ? a.b_int : (region == 1 ? a.b_bnd : a.b_obs);
     double s = 0.0;
-    for (int b = lane; b < nb; b += 32) s += (double)p[(int64_t)b * NSLOT + slot];
+    for (int b = lane; b < nb; b += 32) s += (double)__ldcg(p + (int64_t)b * NSLOT + slot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) tot[q] = s;
@@ -283,7 +328,47 @@ __global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) residual_finish_kernel(FinishArgs a) { finish_body(a); }
+
+// The whole residual stage of a training step in ONE launch: blocks [0, b_int) take the internal points, the next b_bnd
+// the boundary points, the rest the observation points; every block leaves its partial sums in the workspace and takes a
+// ticket, and the block that draws the last ticket reduces all partials in a fixed order (deterministic) into the loss
+// vector and hands the ticket counter back at zero.  The value plane of gy is accumulated with atomics (observation
+// points add to entries the other two roles also write), so the caller zeroes it first (one memset node).
+template <int D, int LAP>
+__global__ void __launch_bounds__(256) residual_step_kernel(ResArgs a, FinishArgs fa, int b_int, int b_bnd, int* ticket) {
+  __shared__ int is_last;
+  float sums[NSLOT];
+#pragma unroll
+  for (int s = 0; s < NSLOT; ++s) sums[s] = 0.0f;
+  const int blk = blockIdx.x;
+  float* dst;
+  if (blk < b_int) {
+    internal_body<D, LAP, true>(a, blk, sums);
+    dst = const_cast<float*>(fa.p_int) + (int64_t)blk * NSLOT;
+  } else if (blk < b_int + b_bnd) {
+    boundary_body<D, true>(a, blk - b_int, sums);
+    dst = const_cast<float*>(fa.p_bnd) + (int64_t)(blk - b_int) * NSLOT;
+  } else {
+    obs_body<D>(a, blk - b_int - b_bnd, sums);
+    dst = const_cast<float*>(fa.p_obs) + (int64_t)(blk - b_int - b_bnd) * NSLOT;
+  }
+  block_reduce_store(sums, dst);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    finish_body(fa);
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
 static inline int blocks_for(int64_t n) { return (int)((n + 255) / 256); }
+static inline int rows_vectorisable(const float* y, const float* gy, int64_t ps, int ldy) {
+  return ldy % 4 == 0 && ps % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0;
+}
 
 }  // namespace pcfd
 
@@ -312,6 +397,7 @@ extern "C" int pcfd_residual_loss_w(const float* data, int32_t n_geom, int64_t n
   a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = boundary_ids; a.nb = nb; a.obs_ids = obs_ids; a.no = no;
   a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = y_bnd; a.ldy = ldy; a.gy_int = gy_int; a.gy_bnd = gy_bnd;
   a.p = *prm; a.n_geom = n_geom; a.wdev = weights_dev; a.fields = nullptr; a.visc_extra = visc_extra; a.gvisc = gvisc;
+  a.vec_rows = rows_vectorisable(y_int, gy_int, y_plane_stride, ldy);
   a.inv_int = 1.0f / (float)((double)n_geom * ni);
   a.inv_bnd = 1.0f / (float)((double)n_geom * nb);
   a.inv_obs = no > 0 ? 1.0f / (float)((double)n_geom * no) : 0.0f;
@@ -361,6 +447,66 @@ extern "C" int pcfd_residual_loss(const float* data, int32_t n_geom, int64_t n_r
                               workspace_bytes, stream);
 }
 
+// The residual stage of a training step in one kernel (+ one memset node): same results as pcfd_residual_loss_w.
+// `ticket`: one int32 that is zero before the first call; the kernel leaves it at zero (the caller keeps it allocated
+// and never shares it between streams).  gy_int plane 0 and gy_bnd are zeroed here (cudaMemsetAsync on `stream`).
+extern "C" int pcfd_residual_step(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
+                                  const int64_t* internal_ids, int64_t ni, const int64_t* boundary_ids, int64_t nb,
+                                  const int64_t* obs_ids, int64_t no, const float* y_int, int64_t y_plane_stride,
+                                  const float* y_bnd, int32_t ldy, const pcfd_residual_params_t* prm,
+                                  const float* weights_dev, const float* visc_extra, float* gvisc, float* gy_int,
+                                  float* gy_bnd, float* out, int32_t* ticket, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (!data || !internal_ids || !boundary_ids || !y_int || !y_bnd || !prm || !gy_int || !gy_bnd || !out || !workspace || !ticket)
+    return PCFD_ERR_ARG;
+  if (n_geom <= 0 || ni <= 0 || nb <= 0 || (prm->dims != 2 && prm->dims != 3) || ldy < prm->dims + 1) return PCFD_ERR_ARG;
+  if (workspace_bytes < pcfd_residual_workspace_bytes(n_geom, ni, nb, no)) return PCFD_ERR_WORKSPACE;
+  const bool data_loss = prm->enable_data_loss && no > 0;
+  if (data_loss && !obs_ids) return PCFD_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  ResArgs a;
+  a.data = data; a.n_rows = n_rows; a.f = f;
+  a.internal_ids = internal_ids; a.ni = ni; a.boundary_ids = boundary_ids; a.nb = nb; a.obs_ids = obs_ids; a.no = no;
+  a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = y_bnd; a.ldy = ldy; a.gy_int = gy_int; a.gy_bnd = gy_bnd;
+  a.p = *prm; a.n_geom = n_geom; a.wdev = weights_dev; a.fields = nullptr; a.visc_extra = visc_extra; a.gvisc = gvisc;
+  a.vec_rows = rows_vectorisable(y_int, gy_int, y_plane_stride, ldy);
+  a.inv_int = 1.0f / (float)((double)n_geom * ni);
+  a.inv_bnd = 1.0f / (float)((double)n_geom * nb);
+  a.inv_obs = no > 0 ? 1.0f / (float)((double)n_geom * no) : 0.0f;
+  a.partial = nullptr;
+  float* ws = reinterpret_cast<float*>(workspace);
+  const int b_int = blocks_for((int64_t)n_geom * ni), b_bnd = blocks_for((int64_t)n_geom * nb);
+  const int b_obs = data_loss ? blocks_for((int64_t)n_geom * no) : 0;
+  FinishArgs fa;
+  fa.p_int = ws; fa.b_int = b_int; fa.p_bnd = ws + (size_t)b_int * NSLOT; fa.b_bnd = b_bnd;
+  fa.p_obs = fa.p_bnd + (size_t)b_bnd * NSLOT; fa.b_obs = b_obs;
+  const int D = prm->dims;
+  fa.dims = D; fa.data_loss = data_loss ? 1 : 0;
+  fa.inv_int = a.inv_int; fa.inv_bnd = a.inv_bnd; fa.inv_obs = a.inv_obs;
+  fa.inv_all = 1.0f / (float)((double)n_geom * (ni + nb));
+  for (int i = 0; i < 16; ++i) fa.weights[i] = prm->weights[i];
+  fa.wdev = weights_dev;
+  fa.out = out;
+  // value plane of gy: accumulated with atomics by all three roles.  When the two buffers are adjacent (ops.py allocates
+  // them as one block: [gy_bnd | gy_int]) one memset covers both.
+  const size_t bytes_int = (size_t)n_geom * ni * ldy * sizeof(float), bytes_bnd = (size_t)n_geom * nb * ldy * sizeof(float);
+  cudaError_t e;
+  if (reinterpret_cast<char*>(gy_bnd) + bytes_bnd == reinterpret_cast<char*>(gy_int)) {
+    e = cudaMemsetAsync(gy_bnd, 0, bytes_bnd + bytes_int, st);
+  } else {
+    e = cudaMemsetAsync(gy_bnd, 0, bytes_bnd, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gy_int, 0, bytes_int, st);
+  }
+  if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
+  const int grid = b_int + b_bnd + b_obs;
+  if (D == 2 && prm->lap_mode == PCFD_LAP_REFERENCE) residual_step_kernel<2, PCFD_LAP_REFERENCE><<<grid, 256, 0, st>>>(a, fa, b_int, b_bnd, ticket);
+  else if (D == 2) residual_step_kernel<2, PCFD_LAP_TRUE><<<grid, 256, 0, st>>>(a, fa, b_int, b_bnd, ticket);
+  else if (prm->lap_mode == PCFD_LAP_REFERENCE) residual_step_kernel<3, PCFD_LAP_REFERENCE><<<grid, 256, 0, st>>>(a, fa, b_int, b_bnd, ticket);
+  else residual_step_kernel<3, PCFD_LAP_TRUE><<<grid, 256, 0, st>>>(a, fa, b_int, b_bnd, ticket);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
 // Per-point residual map of the internal points (predict_step with verbose_predict, models/model_base.py:233-252):
 // fields [n_geom*ni][D+1] = (momentum residual x D, divergence).
 extern "C" int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n_rows, int32_t f,
@@ -375,6 +521,7 @@ extern "C" int pcfd_residual_fields(const float* data, int32_t n_geom, int64_t n
   a.y_int = y_int; a.ps = y_plane_stride; a.y_bnd = nullptr; a.ldy = ldy; a.gy_int = nullptr; a.gy_bnd = nullptr;
   a.p = *prm; a.n_geom = n_geom; a.wdev = nullptr; a.fields = fields; a.partial = nullptr;
   a.visc_extra = nullptr; a.gvisc = nullptr;
+  a.vec_rows = rows_vectorisable(y_int, nullptr, y_plane_stride, ldy);
   a.inv_int = 1.0f / (float)((double)n_geom * ni); a.inv_bnd = 0.0f; a.inv_obs = 0.0f;
   const int b_int = blocks_for((int64_t)n_geom * ni);
   const int D = prm->dims;

@@ -403,18 +403,46 @@ def residual_loss(data: Tensor, internal_ids: Tensor, boundary_ids: Tensor, obs_
     b, n_rows, f = data.shape
     ni, nb = internal_ids.shape[1], boundary_ids.shape[1]
     no = obs_ids.shape[1] if obs_ids is not None else 0
-    gy_int = Jet(torch.empty_like(y_int.t), y_int.width)
-    gy_bnd = Jet(torch.empty_like(y_bnd.t), y_bnd.width)
+    # one block [gy_bnd | gy_int]: the value planes the fused kernel accumulates into are adjacent -> one memset node
+    n_bnd, n_int = y_bnd.t.numel(), y_int.t.numel()
+    block = torch.empty(n_bnd + n_int, dtype=torch.float32, device=data.device)
+    gy_bnd = Jet(block[:n_bnd].view(y_bnd.t.shape), y_bnd.width)
+    gy_int = Jet(block[n_bnd:].view(y_int.t.shape), y_int.width)
     out = torch.empty(_lib.LOSS_OUT_FLOATS, dtype=torch.float32, device=data.device)
-    _lib.launches += 4
     with _timed('residual_loss', 8.0 * b * ni * y_int.cj * y_int.ld + 4.0 * b * ni * f + 8.0 * b * nb * y_int.ld):
-      check(lib.pcfd_residual_loss_w(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
+      if FUSED_RESIDUAL and y_int.t.is_contiguous() and y_bnd.t.is_contiguous():
+        _lib.launches += 1
+        check(lib.pcfd_residual_step(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
+                                     nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
+                                     y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), _ptr(weights_dev), _ptr(visc_extra),
+                                     _ptr(gvisc), gy_int.t.data_ptr(), gy_bnd.t.data_ptr(), out.data_ptr(),
+                                     _residual_ticket(data.device).data_ptr(), workspace.data_ptr(),
+                                     workspace.numel() * workspace.element_size(), _stream()), 'pcfd_residual_step')
+      else:
+        _lib.launches += 4
+        check(lib.pcfd_residual_loss_w(data.data_ptr(), b, n_rows, f, internal_ids.data_ptr(), ni, boundary_ids.data_ptr(),
                                    nb, _ptr(obs_ids) if no > 0 else None, no, y_int.t.data_ptr(), y_int.plane_stride,
                                    y_bnd.t.data_ptr(), y_int.ld, C.byref(prm), _ptr(weights_dev), _ptr(visc_extra),
                                    _ptr(gvisc), gy_int.t.data_ptr(),
                                    gy_bnd.t.data_ptr(), out.data_ptr(), workspace.data_ptr(),
                                    workspace.numel() * workspace.element_size(), _stream()), 'pcfd_residual_loss_w')
     return gy_int, gy_bnd, out
+
+
+# PCFD_FUSED_RESIDUAL=0: the four-launch form of the residual stage (pcfd_residual_loss_w), kept as the independent
+# implementation the fused kernel is tested against
+FUSED_RESIDUAL = os.environ.get('PCFD_FUSED_RESIDUAL', '1') != '0'
+_TICKETS: dict = {}
+
+
+def _residual_ticket(device) -> Tensor:
+    """The last-block ticket of pcfd_residual_step: one zero-initialised int32 per (device, stream); the kernel hands it
+    back at zero."""
+    key = (str(device), _stream())
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
 
 
 def residual_fields(data: Tensor, internal_ids: Tensor, y_int: Jet, prm: ResidualParams) -> Tensor:

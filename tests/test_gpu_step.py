@@ -515,3 +515,32 @@ def test_wide_layers_run_on_the_tensor_cores():
         assert ops.FALLBACKS == []
     finally:
         ops.AUDIT = False
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['tiny_pipn_pp', 'tiny_manufactured_pp', 'tiny_pigano'])
+@pytest.mark.parametrize('mode', ['reference', 'true'])
+def test_one_launch_residual_equals_the_four_launch_form(name, mode):
+    """pcfd_residual_step (one kernel: roles by block, last-block reduction, atomically accumulated value plane) against
+    pcfd_residual_loss_w (internal / boundary / observation / finish kernels) inside the same step: every loss term, the
+    MAE log values and the whole parameter gradient."""
+    from porous_cfd_b200 import ops
+    spec = synthetic.model_spec(name)
+    _, _, params, _ = load_fixture(name)
+    labels = synthetic.build_labels(spec['layout'])
+    data, _, domain = synthetic.make_batch(spec['layout'], seed=77, **TINY_SHAPE)
+    batch = FoamData(data, labels, domain).to('cuda')
+    outs = {}
+    for fused in (True, False):
+        ops.FUSED_RESIDUAL = fused
+        try:
+            model = cuda_model(spec, params)
+            for rep in range(2):          # twice: the ticket counter must come back at zero
+                res = model.fused_step(batch, laplacian=mode)
+            outs[fused] = (res.out.clone(), model.executor.flat_grad.clone())
+        finally:
+            ops.FUSED_RESIDUAL = True
+    torch.cuda.synchronize()
+    a, b = outs[True], outs[False]
+    assert float((a[0] - b[0]).abs().max()) <= 2e-6 * float(b[0].abs().max())
+    assert rel_l2(a[1].double().cpu(), b[1].double().cpu()) < 2e-6
