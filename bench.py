@@ -194,6 +194,52 @@ def _emit(line: dict):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + '\n').encode())
 
 
+def geometry_cache_leg(model, trainer, dev_batches, labels, b: int, ni: int, steps: int) -> dict:
+    """SURVEY 8f rank 4, second half, NEVER part of the headline: training steps fed from an HBM-resident dataset
+    (DeviceFoamDataset.batch -> model.training_step [CUDA graph] -> backward -> Adam), once with FPS / ball query inside
+    every step and once with the per-geometry cache (valid because the FPS start is fixed, see build_geometry_cache)."""
+    from porous_cfd_b200.dataset.device_dataset import DeviceFoamDataset
+    data = torch.cat([d.data for d in dev_batches])
+    domain = {k: torch.cat([d.domain[k] for d in dev_batches]) for k in dev_batches[0].domain}
+    gen = torch.Generator().manual_seed(1)
+    ids = [torch.randperm(data.shape[0], generator=gen)[:b].cuda() for _ in range(8)]
+    model.cuda_graph = True
+    model.pipeline_geometry = False
+    params = list(model.parameters())
+    out = {}
+    for mode in ('uncached', 'cached'):
+        ds = DeviceFoamDataset(data, labels, domain)
+        if mode == 'cached':
+            t0 = time.perf_counter()
+            ds.build_geometry_cache(model)
+            torch.cuda.synchronize()
+            out['build_ms'] = 1e3 * (time.perf_counter() - t0)
+            out['cached_geometries'] = len(ds)
+
+        def one(i):
+            loss = model.training_step(ds.batch(ids[i % 8]), i)
+            for p in params:
+                p.grad = None
+            loss.backward()
+            trainer.step(model.executor.last_flat_grad)
+
+        for i in range(4):
+            one(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            one(4 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {'ms_per_step': ms, 'points_per_s': b * ni / (ms / 1e3)}
+    out['note'] = ('both legs: batches collated on the device from an HBM-resident dataset, step replayed from a CUDA graph, no '
+                   'one-step-ahead geometry pipeline; cached = FPS / ball query taken from the per-geometry cache (exact only '
+                   'with the deterministic FPS start this build uses; the reference re-draws a random start every step)')
+    return out
+
+
 def ingest_leg(dev_batches, labels, n_internal, dims, peaks):
     """SURVEY 8f rank 4, outside the timed step: collation of HBM-resident geometries (pcfd_gather_blocks) and the
     signed-distance feature (pcfd_sdf_feature) on this workload's shapes, CUDA events on the launching stream."""
@@ -547,7 +593,7 @@ def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int,
            'launches_per_step': (launches_per_micro + 1 + (1 if pipelined else 0)) * micro + 2 + (1 if micro > 1 else 0),
            'fallbacks': list(ops.FALLBACKS), 'b_micro': b_micro, 'micro': micro,
            'roofline': family_roofline(fam, prof_steps, env.peaks, engine_name) if rank == 0 else None,
-           'dev_batches': dev_batches, 'labels': labels, 'spec': spec}
+           'dev_batches': dev_batches, 'labels': labels, 'spec': spec, 'model': model, 'trainer': trainer}
     if e2e:
         out['e2e_value'] = pts_per_step * K / (ms_e2e_m / 1e3)
         out['e2e_ms_per_step'] = ms_e2e_m / K
@@ -654,6 +700,9 @@ def main():
     if env.world == 1:
         try:
             ingest = ingest_leg(r['dev_batches'], r['labels'], shape['n_internal'], r['spec']['dims'], env.peaks)
+            if r['model'].executor.uses_geometry() and not args.no_graph:
+                ingest['geometry_cache'] = geometry_cache_leg(r['model'], r['trainer'], r['dev_batches'], r['labels'], b_per_gpu,
+                                                              shape['n_internal'], r['steps'])
         except Exception as e:      # an auxiliary measurement must not cost the bench line
             ingest = {'error': f'{type(e).__name__}: {e}'}
             torch.cuda.synchronize()

@@ -234,8 +234,19 @@ int pcfd_ball_query(const float* pos, const int64_t* centroid_idx, int32_t n_geo
 int pcfd_sa_edges(const int32_t* nbr, int64_t m_total, int32_t k, int64_t n_points_total,
                   int32_t* slots, void* stream);
 /*
+ * Set-abstraction geometry of a batch from a per-geometry cache (the dataset is sampled once,
+ * dataset/foam_dataset.py:159-161, so FPS centroids and ball-query neighbourhoods of a geometry never change).
+ * idx_local [n_geom][m] (int64) and nbr_local [n_geom][m][k] (int32, -1 = empty) hold indices local to their geometry
+ * (0 .. n-1) for the geometries of THIS batch, in batch order; the call rebases them to the flattened numbering of the
+ * batch and builds the edge slots with the rule of pcfd_sa_edges: idx [n_geom*m], slots [n_geom*m][k+1].
+ */
+int pcfd_sa_cached_geometry(const int64_t* idx_local, const int32_t* nbr_local, int32_t n_geom, int32_t m, int32_t k,
+                            int32_t n, int64_t* idx, int32_t* slots, void* stream);
+/*
  * Edge features (PointConvNext.message, models/modules.py:286-292):
  *   ein[(i,s)] = [ x[j][0:f_in], pos[j] - pos[centroid_i] / r ],  j = slots[i][s]; zeros if empty.
+ * ein rows are written 16 bytes at a time: ein 16-byte aligned, ldein a multiple of 4 (>= f_in + dims); the pad columns
+ * of a row are set to zero.
  */
 int pcfd_sa_gather(const float* x, int32_t ldx, int32_t f_in, const float* pos, int32_t dims,
                    const int64_t* centroid_idx, const int32_t* slots, int64_t m_total, int32_t kp, float r,

@@ -75,6 +75,7 @@ SIGNATURES = {
     'pcfd_fps_ws': (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P, C.c_size_t, _P]),
     'pcfd_ball_query': (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P, _P]),
     'pcfd_sa_edges': (C.c_int, [_P, _I64, _I32, _I64, _P, _P]),
+    'pcfd_sa_cached_geometry': (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     'pcfd_sa_gather': (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _I64, _I32, _F, _P, _I32, _P]),
     'pcfd_sa_scatter_bwd': (C.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _I32, _P]),
     'pcfd_gather_cols': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _I64, C.POINTER(C.c_int32), _I32, _P, _I32,

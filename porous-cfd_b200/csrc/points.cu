@@ -308,27 +308,61 @@ __global__ void sa_edges_kernel(const int32_t* __restrict__ nbr, int64_t m_total
   for (; w < kp; ++w) slots[i * kp + w] = -1;
 }
 
-__global__ void sa_gather_kernel(const float* __restrict__ x, int ldx, int f_in, const float* __restrict__ pos,
+// Set-abstraction geometry of a batch from a per-geometry cache (DeviceFoamDataset.build_geometry_cache): FPS centroids
+// and ball-query neighbours are stored with indices LOCAL to their geometry; this kernel rebases them to the flattened
+// point numbering of the batch (geometry g of the batch owns points [g*n, (g+1)*n)) and applies the same self-loop rule as
+// sa_edges_kernel (which depends on the position of a geometry inside the batch, so slots cannot be cached themselves).
+__global__ void sa_cached_geometry_kernel(const int64_t* __restrict__ idx_local, const int32_t* __restrict__ nbr_local,
+                                          int64_t m_total, int m, int k, int n, int64_t n_points_total,
+                                          int64_t* __restrict__ idx, int32_t* __restrict__ slots) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m_total) return;
+  const int64_t base = (i / m) * n;
+  idx[i] = idx_local[i] + base;
+  const int kp = k + 1;
+  int w = 0;
+  for (int j = 0; j < k; ++j) {
+    const int v = nbr_local[i * k + j];
+    if (v >= 0 && (int64_t)v + base != i) slots[i * kp + w++] = (int32_t)(v + base);
+  }
+  if (i < n_points_total) slots[i * kp + w++] = (int32_t)i;
+  for (; w < kp; ++w) slots[i * kp + w] = -1;
+}
+
+// one thread per (edge, chunk of 4 output columns): 16-byte stores into the 16-byte aligned rows of ein, and a 16-byte
+// load where the chunk lies inside the feature block of an aligned x row (the 128-wide level-1 features); pad columns = 0
+__global__ void __launch_bounds__(256) sa_gather_kernel(const float* __restrict__ x, int ldx, int f_in, const float* __restrict__ pos,
                                  int dims, const int64_t* __restrict__ cidx, const int32_t* __restrict__ slots,
-                                 int64_t n_edges, int kp, float r, float* __restrict__ ein, int ldein) {
+                                 int64_t n_edges, int kp, float r, float* __restrict__ ein, int ldein, int x_vec) {
   const int width = f_in + dims;
+  const int chunks = ldein >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_edges * width) return;
-  const int64_t e = t / width;
-  const int col = (int)(t % width);
-  const int j = slots[e];
-  float v = 0.0f;
+  if (t >= n_edges * chunks) return;
+  const int64_t e = t / chunks;
+  const int col0 = (int)(t - e * chunks) * 4;
+  const int j = __ldg(slots + e);
+  float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if (j >= 0) {
-    if (col < f_in) {
-      v = __ldg(x + (int64_t)j * ldx + col);
+    if (x_vec && col0 + 4 <= f_in) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(x + (int64_t)j * ldx + col0));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
     } else {
-      const int d = col - f_in;
-      const int64_t ci = cidx[e / kp];
-      // reference operator precedence: pos_j - (pos_i / r)   (models/modules.py:287)
-      v = __fsub_rn(__ldg(pos + (int64_t)j * dims + d), __fdiv_rn(__ldg(pos + ci * dims + d), r));
+      int64_t ci = -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int col = col0 + u;
+        if (col < f_in) {
+          v[u] = __ldg(x + (int64_t)j * ldx + col);
+        } else if (col < width) {
+          const int d = col - f_in;
+          if (ci < 0) ci = __ldg(cidx + e / kp);
+          // reference operator precedence: pos_j - (pos_i / r)   (models/modules.py:287)
+          v[u] = __fsub_rn(__ldg(pos + (int64_t)j * dims + d), __fdiv_rn(__ldg(pos + ci * dims + d), r));
+        }
+      }
     }
   }
-  ein[e * ldein + col] = v;
+  *reinterpret_cast<float4*>(ein + e * ldein + col0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 __global__ void sa_scatter_bwd_kernel(const float* __restrict__ gein, int ldgein, const int32_t* __restrict__ slots,
@@ -534,14 +568,27 @@ extern "C" int pcfd_sa_edges(const int32_t* nbr, int64_t m_total, int32_t k, int
   return PCFD_OK;
 }
 
+extern "C" int pcfd_sa_cached_geometry(const int64_t* idx_local, const int32_t* nbr_local, int32_t n_geom, int32_t m,
+                                       int32_t k, int32_t n, int64_t* idx, int32_t* slots, void* stream) {
+  if (!idx_local || !nbr_local || !idx || !slots || n_geom <= 0 || m <= 0 || k <= 0 || n <= 0) return PCFD_ERR_ARG;
+  if ((int64_t)n_geom * n >= ((int64_t)1 << 31)) return PCFD_ERR_ARG;
+  const int64_t m_total = (int64_t)n_geom * m;
+  sa_cached_geometry_kernel<<<(unsigned)((m_total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      idx_local, nbr_local, m_total, m, k, n, (int64_t)n_geom * n, idx, slots);
+  PCFD_CHECK_LAUNCH();
+  return PCFD_OK;
+}
+
 extern "C" int pcfd_sa_gather(const float* x, int32_t ldx, int32_t f_in, const float* pos, int32_t dims,
                               const int64_t* centroid_idx, const int32_t* slots, int64_t m_total, int32_t kp, float r,
                               float* ein, int32_t ldein, void* stream) {
   if (!pos || !centroid_idx || !slots || !ein || m_total <= 0 || kp <= 0 || f_in < 0 || (f_in > 0 && !x))
     return PCFD_ERR_ARG;
-  const int64_t total = m_total * kp * (f_in + dims);
+  if (ldein % 4 != 0 || ldein < f_in + dims || (reinterpret_cast<uintptr_t>(ein) & 15) != 0) return PCFD_ERR_ARG;
+  const int64_t total = m_total * kp * (ldein / 4);
+  const int x_vec = x != nullptr && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   sa_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, ldx, f_in, pos, dims, centroid_idx, slots, m_total * kp, kp, r, ein, ldein);
+      x, ldx, f_in, pos, dims, centroid_idx, slots, m_total * kp, kp, r, ein, ldein, x_vec);
   PCFD_CHECK_LAUNCH();
   return PCFD_OK;
 }

@@ -432,7 +432,7 @@ static int launch_dx(const float* gzout, int64_t gzout_ps, int ldgzout, const fl
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
   }
   const int total = a.row_tiles * a.k_passes;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = balanced_grid(total);
   const cudaError_t le = launch_pdl(ws_dx_kernel<CJ, NT>, dim3(grid), dim3(DX_THREADS), (size_t)SMEM, st, tmG, tmW, tmO, a);
   if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;

@@ -345,7 +345,7 @@ static int launch_fwd(const float* zin, int64_t zin_ps, int ldzin, const float* 
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
   }
   const int total = a.row_tiles * a.n_passes;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = balanced_grid(total);
   const cudaError_t le = launch_pdl(ws_fwd_kernel<CJ, NT>, dim3(grid), dim3(THREADS), (size_t)SMEM, st, tmZ, tmW, tmO, a);
   if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;

@@ -338,7 +338,7 @@ static int launch_fwd1(const float* zin, int ldzin, const float* w, int ldw, flo
     if (e != cudaSuccess) return PCFD_ERR_CUDA + (int)e;
   }
   const int total = a.row_tiles * a.n_passes;
-  const int grid = total < num_sms() ? total : num_sms();
+  const int grid = balanced_grid(total);
   const cudaError_t le = launch_pdl(ws_fwd1_kernel<NT>, dim3(grid), dim3(F1_THREADS), (size_t)SMEM, st, tmZ, tmW, tmO, a);
   if (le != cudaSuccess) return PCFD_ERR_CUDA + (int)le;
   return PCFD_OK;

@@ -32,6 +32,7 @@ class DeviceFoamDataset:
         self.data = data.to(device=device, dtype=torch.float32).contiguous()
         self.labels = labels
         self.domain = {k: v.to(device=device, dtype=torch.int64).contiguous() for k, v in domain.items()}
+        self.geo_cache = None
 
     @classmethod
     def from_samples(cls, samples: Sequence[FoamData], device='cuda') -> 'DeviceFoamDataset':
@@ -71,11 +72,66 @@ class DeviceFoamDataset:
         cls = boundary_class.to(device=self.data.device, dtype=torch.int32).contiguous()
         ops.boundary_one_hot(self.data, self._n_internal(), cls, len(cols), cols[0])
 
+    # ---- per-geometry cache of the set-abstraction geometry (second half) ----------------------
+    def build_geometry_cache(self, model, chunk: int = 64) -> None:
+        """FPS centroids and ball-query neighbourhoods of every resident geometry, for `model`'s set-abstraction stack.
+
+        The reference samples its point clouds once (`FoamDataset.__init__`, dataset/foam_dataset.py:159-161), so the
+        encoder's FPS / radius results of a geometry are the same in every epoch -- PROVIDED the FPS start is fixed.
+        `torch_cluster.fps` defaults to a random start (which the reference does not override); this build uses the first
+        point (oracle/pyg_restate.py), and only under that documented deviation is the cache exact.  Opt-in: batches made
+        after this call carry `FoamData.geometry`, which the training step uses instead of running FPS / ball query.
+        Indices are stored local to their geometry; the edge slots depend on a geometry's position in the batch (PyG's
+        bipartite self-loop rule) and are rebuilt per batch by one launch per level (pcfd_sa_cached_geometry)."""
+        from ..engine import sa_geometry_levels
+        ex = model.executor
+        if not ex.uses_geometry():
+            raise ValueError('this model has no set-abstraction encoder: nothing to cache')
+        stack = ex.plan['sa_stack']
+        g_total = len(self)
+        levels = None
+        for lo in range(0, g_total, chunk):
+            sl = slice(lo, min(g_total, lo + chunk))
+            dom = {k: v[sl] for k, v in self.domain.items()}
+            pos = ex.geometry_positions(self.data[sl], self.labels, dom)
+            lv = sa_geometry_levels(stack, pos)
+            if levels is None:
+                levels = [{'idx': [], 'nbr': [], 'newpos': [], 'n': v['n']} for v in lv]
+            b = pos.shape[0]
+            for acc, v in zip(levels, lv):
+                m = v['idx'].shape[1]
+                base = (torch.arange(b, device=pos.device) * v['n']).view(b, 1)
+                acc['idx'].append(v['idx'] - base)
+                nbr = v['nbr'].view(b, m, -1)
+                acc['nbr'].append(torch.where(nbr >= 0, nbr - base.view(b, 1, 1).to(torch.int32), nbr))
+                acc['newpos'].append(v['newpos'])
+        self.geo_cache = [{'idx': torch.cat(a['idx']).contiguous(), 'nbr': torch.cat(a['nbr']).contiguous(),
+                           'newpos': torch.cat(a['newpos']).contiguous(), 'n': a['n']} for a in levels]
+        self.geo_cache_key = tuple((l.ratio, l.radius, l.max_neighbors) for l in stack.levels)
+
+    def drop_geometry_cache(self) -> None:
+        self.geo_cache = None
+
+    def _cached_geometry(self, ids: Tensor) -> list:
+        flat = []
+        for lv in self.geo_cache:
+            flat += [lv['idx'], lv['nbr'], lv['newpos']]
+        got = ops.gather_blocks_multi(flat, ids)                                              # one launch
+        geo = []
+        for i, lv in enumerate(self.geo_cache):
+            idx_local, nbr_local, newpos = got[3 * i:3 * i + 3]
+            idx, slots = ops.sa_cached_geometry(idx_local, nbr_local, lv['n'])               # one launch per level
+            geo.append({'idx': idx, 'slots': slots, 'newpos': newpos})
+        return geo
+
     # ---- batches (reference: collate_fn) -----------------------------------------------------------------------
     def _gather(self, ids: Tensor) -> FoamData:
         names = list(self.domain)
         out = ops.gather_blocks_multi([self.data] + [self.domain[k] for k in names], ids)     # one launch
-        return FoamData(out[0], self.labels, dict(zip(names, out[1:])))
+        fd = FoamData(out[0], self.labels, dict(zip(names, out[1:])))
+        if self.geo_cache is not None:
+            fd.geometry = self._cached_geometry(ids)
+        return fd
 
     def batch(self, geometry_ids) -> FoamData:
         """collate_fn of the chosen geometries.  Ids given on the host are range-checked; a CUDA id tensor is used as

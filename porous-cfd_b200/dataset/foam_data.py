@@ -20,6 +20,9 @@ class FoamData:
         self.data = data
         self.labels = labels
         self.domain = domain
+        # optional: the batch's set-abstraction geometry (FPS centroids, edge slots, centroid positions per level) when a
+        # DeviceFoamDataset with a geometry cache built it; the training step then skips FPS / ball query
+        self.geometry = None
 
     # ---- column bookkeeping ---------------------------------------------------------------
     def columns(self, label: str) -> list[int]:

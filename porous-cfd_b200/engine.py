@@ -233,21 +233,31 @@ class SAStack:
     out_features: int = 0
 
 
-def sa_geometry(stack: SAStack, pos0: Tensor) -> list:
-    """The part of the set-abstraction stack that depends on the point positions only (no weights, no features):
-    per level the FPS centroids, the radius neighbourhoods as edge slots, and the centroid positions.  A training loop
-    that knows its next batch can run this for batch t+1 beside the step of batch t (PinnExecutor.geometry)."""
+def sa_geometry_levels(stack: SAStack, pos0: Tensor) -> list:
+    """FPS centroids, ball-query neighbours and centroid positions of every level: per level {'idx' (B, m) int64 and
+    'nbr' (B*m, K) int32, both flattened over the batch, 'newpos' (B, m, D), 'n' points per geometry at this level}."""
     b, n, d = pos0.shape
-    pos, geo = pos0, []
+    pos, out = pos0, []
     for lvl in stack.levels:
         idx = ops.fps(pos, lvl.ratio)
         m = idx.shape[1]
         nbr, _ = ops.ball_query(pos, idx, lvl.radius, lvl.max_neighbors)
-        slots = ops.sa_edges(nbr, b * n)
         newpos = torch.empty((b, m, d), dtype=torch.float32, device=pos.device)
         ops.gather_cols(pos, 1, b * n, d, idx, 0, b * m, list(range(d)), newpos, d, b * m)
-        geo.append({'idx': idx, 'slots': slots, 'newpos': newpos})
+        out.append({'idx': idx, 'nbr': nbr, 'newpos': newpos, 'n': n})
         pos, n = newpos, m
+    return out
+
+
+def sa_geometry(stack: SAStack, pos0: Tensor) -> list:
+    """The part of the set-abstraction stack that depends on the point positions only (no weights, no features):
+    per level the FPS centroids, the radius neighbourhoods as edge slots, and the centroid positions.  A training loop
+    that knows its next batch can run this for batch t+1 beside the step of batch t (PinnExecutor.geometry)."""
+    b = pos0.shape[0]
+    geo = []
+    for lv in sa_geometry_levels(stack, pos0):
+        slots = ops.sa_edges(lv['nbr'], b * lv['n'])
+        geo.append({'idx': lv['idx'], 'slots': slots, 'newpos': lv['newpos']})
     return geo
 
 
@@ -341,15 +351,19 @@ class GraphedStep:
     another).  `run(..., next_data, next_domain)` names the batch the following call will bring; a call whose batch was
     not announced computes its geometry in line first."""
 
-    def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str, pipeline: bool = False):
+    def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str, pipeline: bool = False,
+                 geo: Optional[list] = None):
         self.ex = ex
         self.data = torch.empty_like(data)
         self.domain = {k: torch.empty_like(v) for k, v in domain.items()}
         self.labels = labels
-        self.pipeline = pipeline and ex.uses_geometry()
+        self.cached = geo is not None          # geometry handed in with every batch (DeviceFoamDataset geometry cache)
+        self.pipeline = pipeline and ex.uses_geometry() and not self.cached
         self.load(data, domain)
         self.geo = None
         self.expected = None          # (data, version, boundary ids, version) of the batch whose geometry the static buffers hold
+        if self.cached:
+            self.geo = [{k: v.clone() for k, v in lv.items()} for lv in geo]      # static buffers the graph reads
         if self.pipeline:
             # the only input of the geometry branch: the next batch's sampled positions, gathered into a static buffer
             self.pos_next = ex.geometry_positions(self.data, labels, self.domain)
@@ -369,7 +383,7 @@ class GraphedStep:
                     for k in cur:
                         cur[k].copy_(new[k])
             else:
-                self.result = ex.step(self.data, labels, self.domain, laplacian)
+                self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
 
     def _announced(self, data: Tensor, domain: dict) -> bool:
         """Are these the tensors the previous call announced, unmodified since?  The announced tensors are kept
@@ -389,8 +403,15 @@ class GraphedStep:
         for k, v in domain.items():
             self.domain[k].copy_(v, non_blocking=True)
 
-    def run(self, data: Tensor, domain: dict, next_data: Optional[Tensor] = None, next_domain: Optional[dict] = None) -> 'StepResult':
+    def run(self, data: Tensor, domain: dict, next_data: Optional[Tensor] = None, next_domain: Optional[dict] = None,
+            geo: Optional[list] = None) -> 'StepResult':
         self.load(data, domain)
+        if self.cached:
+            if geo is None:
+                raise _lib.PcfdError('this step graph was captured for batches that bring their cached geometry')
+            for cur, new in zip(self.geo, geo):
+                for k in cur:
+                    cur[k].copy_(new[k], non_blocking=True)
         if self.pipeline:
             if not self._announced(data, domain):
                 # not announced by the previous call: geometry of this batch in line, into the static buffers
@@ -412,8 +433,8 @@ class _EagerStep:
     def __init__(self, ex, labels, laplacian):
         self.ex, self.labels, self.laplacian = ex, labels, laplacian
 
-    def run(self, data, domain, next_data=None, next_domain=None):
-        return self.ex.step(data, self.labels, domain, self.laplacian)
+    def run(self, data, domain, next_data=None, next_domain=None, geo=None):
+        return self.ex.step(data, self.labels, domain, self.laplacian, geo=geo)
 
 
 class PinnExecutor:
@@ -706,34 +727,34 @@ class PinnExecutor:
         return zs[-1]
 
     def graphed_step(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference',
-                     next_batch=None) -> StepResult:
+                     next_batch=None, geo: Optional[list] = None) -> StepResult:
         """`step` replayed from a CUDA graph.  The first call with a given signature runs eagerly (it sizes the
         workspace and the padded weight copies), the second captures, later ones replay; every call is exactly one
         training step (dropout seed, ReLoBRaLo state and gradients advance once)."""
         key = (tuple(data.shape), tuple((k, tuple(v.shape)) for k, v in sorted(domain.items())), tuple(labels),
                laplacian, self.model.training, self.model.enable_data_loss)
-        pipeline = bool(getattr(self.model, 'pipeline_geometry', False))
-        key = key + (pipeline,)
+        pipeline = bool(getattr(self.model, 'pipeline_geometry', False)) and geo is None
+        key = key + (pipeline, geo is not None)
         nd, ndom = (next_batch.data, next_batch.domain) if next_batch is not None else (None, None)
         if nd is not None and (tuple(nd.shape) != tuple(data.shape) or any(tuple(ndom[k].shape) != tuple(v.shape) for k, v in domain.items())):
             nd, ndom = None, None        # a differently shaped next batch (last, smaller one) cannot share the buffers
         g = self._graphs.get(key)
         if g is not None:
-            return g.run(data, domain, nd, ndom)
+            return g.run(data, domain, nd, ndom, geo=geo)
         if key not in self._seen:
             self._seen.add(key)
-            return self.step(data, labels, domain, laplacian)
+            return self.step(data, labels, domain, laplacian, geo=geo)
         try:
-            g = GraphedStep(self, data, labels, domain, laplacian, pipeline)
+            g = GraphedStep(self, data, labels, domain, laplacian, pipeline, geo=geo)
         except RuntimeError as exc:      # an op that cannot be captured: stay on the per-kernel launches for this signature
             import warnings
             warnings.warn(f'CUDA graph capture of the fused step failed ({exc}); launching eagerly')
             torch.cuda.synchronize()
             self._seen.discard(key)
             self._graphs[key] = _EagerStep(self, labels, laplacian)
-            return self._graphs[key].run(data, domain)
+            return self._graphs[key].run(data, domain, geo=geo)
         self._graphs[key] = g
-        return g.run(data, domain, nd, ndom)
+        return g.run(data, domain, nd, ndom, geo=geo)
 
     def predict_with_residuals(self, data: Tensor, labels: dict, domain: dict, laplacian: str = 'reference'):
         """predict_step(verbose): predictions at all points (B, N, D+1) and the residual map of the internal

@@ -277,6 +277,8 @@ class PorousPinnBase(_Base):
         """The hot path without the autograd wrapper: fills `executor.flat_grad`, returns StepResult.  `geo`: the
         batch's set-abstraction geometry when it was computed ahead (`executor.geometry`); `accumulate`: add this
         batch's gradient to the buffer (micro-batches of one optimizer step)."""
+        if geo is None:
+            geo = getattr(batch, 'geometry', None)       # a DeviceFoamDataset batch brings its cached geometry
         return self.executor.step(batch.data, batch.labels, batch.domain, laplacian or self.laplacian, keep_outputs, geo,
                                   accumulate)
 
@@ -288,7 +290,8 @@ class PorousPinnBase(_Base):
     def training_step(self, batch: FoamData, batch_idx: int = 0):
         if self.cuda_graph:
             nxt, self._next_batch = self._next_batch, None
-            res = self.executor.graphed_step(batch.data, batch.labels, batch.domain, self.laplacian, next_batch=nxt)
+            res = self.executor.graphed_step(batch.data, batch.labels, batch.domain, self.laplacian, next_batch=nxt,
+                                             geo=getattr(batch, 'geometry', None))
         else:
             res = self.fused_step(batch)
         self.last_step = res

@@ -344,6 +344,21 @@ def sa_edges(nbr: Tensor, n_points_total: int) -> Tensor:
     return slots
 
 
+def sa_cached_geometry(idx_local: Tensor, nbr_local: Tensor, n: int, idx_out: Optional[Tensor] = None,
+                       slots_out: Optional[Tensor] = None):
+    """idx_local (B, m) int64, nbr_local (B, m, k) int32 (indices local to each geometry of n points) -> (idx (B, m) int64
+    flattened over the batch, slots (B*m, k+1) int32) -- what fps + ball_query + sa_edges produce for the same batch."""
+    lib = _lib.load()
+    b, m = idx_local.shape
+    k = nbr_local.shape[2]
+    idx = idx_out if idx_out is not None else torch.empty((b, m), dtype=torch.int64, device=idx_local.device)
+    slots = slots_out if slots_out is not None else torch.empty((b * m, k + 1), dtype=torch.int32, device=idx_local.device)
+    _lib.launches += 1
+    check(lib.pcfd_sa_cached_geometry(idx_local.data_ptr(), nbr_local.data_ptr(), b, m, k, n, idx.data_ptr(), slots.data_ptr(),
+                                      _stream()), 'pcfd_sa_cached_geometry')
+    return idx, slots
+
+
 def sa_gather(x: Optional[Tensor], ldx: int, f_in: int, pos: Tensor, centroid_idx: Tensor, slots: Tensor,
               r: float) -> Tensor:
     lib = _lib.load()

@@ -113,3 +113,44 @@ def test_training_step_from_a_device_batch():
     l_host = float(model.training_step(host, 0))
     l_dev = float(model.training_step(dev, 0))
     assert l_host == l_dev
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['tiny_pipn_pp', 'tiny_pigano_pp'])
+def test_geometry_cache_reproduces_the_step(name):
+    """SURVEY 8f rank 4, second half: FPS / ball-query results cached per geometry (the dataset is sampled once).  A
+    batch drawn from the cache -- any geometries, any order -- brings exactly the centroids, edge slots and centroid
+    positions that FPS + ball query + the self-loop rule give for that batch, and the training step (eager and from a
+    CUDA graph) gives the same loss and gradients with it."""
+    from helpers import load_fixture, rel_l2
+    from porous_cfd_b200 import factory
+    spec = synthetic.model_spec(name)
+    _, _, params, _ = load_fixture(name)
+    model = factory.build_model(spec)
+    model.load_state_dict(params)
+    model = model.cuda().eval()
+    data, labels, domain = synthetic.make_batch(spec['layout'], 9, 40, 24, 10, seed=4)
+    plain = DeviceFoamDataset(data, labels, domain)
+    cached = DeviceFoamDataset(data, labels, domain)
+    cached.build_geometry_cache(model, chunk=4)          # chunks of 4, 4, 1
+    ex = model.executor
+    for ids in ([3, 0, 7], [8, 8, 1, 2], [5]):
+        want_batch = plain.batch(ids)
+        got_batch = cached.batch(ids)
+        assert want_batch.geometry is None and got_batch.geometry is not None
+        want = ex.geometry(want_batch.data, labels, want_batch.domain)
+        for lw, lg in zip(want, got_batch.geometry):
+            for k in ('idx', 'slots', 'newpos'):
+                assert torch.equal(lw[k], lg[k]), (ids, k)
+        r0 = model.fused_step(want_batch)
+        g0 = ex.flat_grad.clone()
+        r1 = model.fused_step(got_batch)
+        assert torch.equal(r0.out, r1.out) or float((r0.out - r1.out).abs().max()) <= 1e-6 * float(r0.out.abs().max())
+        assert rel_l2(ex.flat_grad.double().cpu(), g0.double().cpu()) < 1e-6
+    # the graphed public path: eager call, capture, replays, all with cached geometry
+    model.cuda_graph = True
+    for step, ids in enumerate(([1, 2, 3], [4, 5, 6], [7, 8, 0], [2, 2, 5])):
+        batch = cached.batch(ids)
+        loss = model.training_step(batch, step)
+        ref = model.executor.step(batch.data, labels, batch.domain, model.laplacian)
+        assert abs(float(loss) - float(ref.loss)) <= 1e-6 * abs(float(ref.loss)), step
