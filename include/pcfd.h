@@ -372,6 +372,28 @@ int pcfd_relobralo_update(const float* losses, int32_t n, float* init_losses, fl
                           int64_t* step, int32_t batch_size, float alpha, float beta, float tau, float eps,
                           uint64_t seed, float* weights_out, void* stream);
 
+/* Data-parallel optimizer tail in one kernel over NVLink / NVSwitch peer memory (csrc/dp_adam.cu): gradient
+ * reduce-scatter + Adam on this rank's slice + all-gather of the new parameters, replacing ncclAllReduce(flat gradient)
+ * followed by pcfd_adam_step (reference: Lightning DDP + torch.optim.Adam, common/training.py:66-71,83).
+ * `peers`: for every rank r < world the address, IN THIS PROCESS, of rank r's flat gradient, flat parameters and flag
+ * array (symmetric memory: same sizes on every rank, peer-mapped; buffers padded to a multiple of 4 floats and 16-byte
+ * aligned), plus the multicast addresses of the gradient and parameter buffers (both NULL: peer loads / stores instead
+ * of multimem.ld_reduce / multimem.st).  The flag array holds pcfd_dp_flags_len() uint32, zero before the first call.
+ * `epoch`: 4 int32 of local device memory, zero before the first call ([2] != 0 afterwards = a peer did not arrive
+ * within ~2 s).  Every rank must call this once per step with the same n and hyper-parameters; exp_avg / exp_avg_sq
+ * are full-size local buffers of which only this rank's slice is used.  grad_scale = 1 / (world * micro-batches). */
+typedef struct {
+  void* grad[16];
+  void* param[16];
+  void* flags[16];
+  void* grad_mc;
+  void* param_mc;
+  int32_t rank, world;
+} pcfd_dp_peers_t;
+int32_t pcfd_dp_flags_len(void);
+int pcfd_dp_adam_step(const pcfd_dp_peers_t* peers, float* exp_avg, float* exp_avg_sq, int64_t* step, const float* lr,
+                      float beta1, float beta2, float eps, float grad_scale, int64_t n, int32_t* epoch, void* stream);
+
 /* torch.optim.Adam (no weight decay, no amsgrad; models/pipn/pipn_foam.py:102-105 configure_optimizers) on flat
  * fp32 buffers: step += 1; m, v, param updated in one pass.  `step` (int64) and `lr` (float) are device scalars so
  * that the launch is graph-capturable; `grad_scale` multiplies the gradient first (1/world after an all-reduce). */

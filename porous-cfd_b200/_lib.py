@@ -31,6 +31,11 @@ class InTrans(C.Structure):
                 ('drop_p', C.c_float), ('seed_dev', C.c_void_p), ('salt', C.c_uint32), ('reserved', C.c_uint32)]
 
 
+class DpPeers(C.Structure):
+    _fields_ = [('grad', C.c_void_p * 16), ('param', C.c_void_p * 16), ('flags', C.c_void_p * 16), ('grad_mc', C.c_void_p),
+                ('param_mc', C.c_void_p), ('rank', C.c_int32), ('world', C.c_int32)]
+
+
 class ResidualParams(C.Structure):
     _fields_ = [('dims', C.c_int32), ('loss_kind', C.c_int32), ('lap_mode', C.c_int32), ('enable_data_loss', C.c_int32),
                 ('nu', C.c_float), ('d', C.c_float), ('f', C.c_float),
@@ -91,6 +96,8 @@ SIGNATURES = {
     'pcfd_residual_fields': (C.c_int, [_P, _I32, _I64, _I32, _P, _I64, _P, _I64, _I32, C.POINTER(ResidualParams), _P, _P]),
     'pcfd_residual_eval': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(ResidualParams), _P, _P, _P]),
     'pcfd_mean_squares': (C.c_int, [_P, _I64, _I32, _P, _P]),
+    'pcfd_dp_flags_len': (_I32, []),
+    'pcfd_dp_adam_step': (C.c_int, [C.POINTER(DpPeers), _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P, _P]),
     'pcfd_adam_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I64, _P]),
     'pcfd_relobralo_update': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F, _F, _F, _F, C.c_uint64, _P, _P]),
     'pcfd_sdf_feature': (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),

@@ -59,7 +59,10 @@ class FlatAdamTrainer:
     whole GPU one after the other, the weight-gradient queue drains at the very end of the reverse pass, and the only
     gradients that are final early (the last two decoder layers) are 6 % of the buffer."""
 
-    def __init__(self, model, process_group=None):
+    def __init__(self, model, process_group=None, fused_dp: Optional[bool] = None):
+        """`fused_dp`: at world > 1 use the one-kernel optimizer tail over peer memory (pcfd_dp_adam_step) instead of
+        NCCL all-reduce + Adam.  Default: on when torch's symmetric memory is available for the group (PCFD_FUSED_DP=0
+        switches it off); False forces the NCCL path (the independent implementation the fused kernel is tested against)."""
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -67,7 +70,18 @@ class FlatAdamTrainer:
         # re-point every parameter into one flat buffer (same order as the executor's flat gradient) so that Adam is a
         # single fused launch
         total = ex.flat_grad.numel()
-        self.flat_param = torch.empty(total, dtype=torch.float32, device=ex.device)
+        self.dp = None
+        if fused_dp is None:
+            fused_dp = os.environ.get('PCFD_FUSED_DP', '1') != '0'
+        if self.world > 1 and fused_dp:
+            try:
+                self._setup_symmetric(ex, total)
+            except Exception as exc:      # no symmetric memory on this box / build: NCCL all-reduce + Adam
+                import warnings
+                warnings.warn(f'fused data-parallel optimizer tail unavailable ({type(exc).__name__}: {exc}); using NCCL')
+                self.dp = None
+        if self.dp is None:
+            self.flat_param = torch.empty(total, dtype=torch.float32, device=ex.device)
         off = 0
         for p in ex.params:
             n = p.numel()
@@ -87,9 +101,45 @@ class FlatAdamTrainer:
         self.lr_dev = torch.full((1,), float(g['lr']), dtype=torch.float32, device=ex.device)
         self.optimizer = self     # `.optimizer.step()` of the earlier torch.optim-based trainer keeps working
         self.accumulate = 1       # micro-batches per optimizer step (their gradients are summed; 1/accumulate in Adam)
+        if self.dp is not None:   # moments padded like the symmetric buffers (float4 units)
+            pad = self.dp['n_pad'] - total
+            if pad:
+                self.exp_avg = torch.zeros(self.dp['n_pad'], dtype=torch.float32, device=ex.device)[:total]
+                self.exp_avg_sq = torch.zeros(self.dp['n_pad'], dtype=torch.float32, device=ex.device)[:total]
+
+    def _setup_symmetric(self, ex, total: int) -> None:
+        """Flat gradient, flat parameters and the barrier flags in symmetric memory; peers' addresses into a DpPeers."""
+        import torch.distributed._symmetric_memory as symm_mem
+        from .. import _lib
+        group = self.group if self.group is not None else dist.group.WORLD
+        name = group.group_name
+        n_pad = (total + 3) // 4 * 4
+        dev = ex.device
+        g = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+        p = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+        f = symm_mem.empty(int(_lib.load().pcfd_dp_flags_len()), dtype=torch.int32, device=dev)
+        g.zero_()
+        p.zero_()
+        f.zero_()
+        hg, hp, hf = (symm_mem.rendezvous(t, name) for t in (g, p, f))
+        peers = _lib.DpPeers()
+        for r in range(self.world):
+            peers.grad[r], peers.param[r], peers.flags[r] = hg.buffer_ptrs[r], hp.buffer_ptrs[r], hf.buffer_ptrs[r]
+        use_mc = os.environ.get('PCFD_DP_MULTIMEM', '1') != '0' and hg.multicast_ptr and hp.multicast_ptr
+        peers.grad_mc = hg.multicast_ptr if use_mc else None
+        peers.param_mc = hp.multicast_ptr if use_mc else None
+        peers.rank, peers.world = hg.rank, self.world
+        self.flat_param = p[:total]
+        ex.rebind_flat_grad(g[:total])
+        torch.cuda.synchronize()
+        hf.barrier()              # every rank's buffers are zeroed before any peer touches them
+        self.dp = {'peers': peers, 'handles': (hg, hp, hf), 'buffers': (g, p, f), 'n_pad': n_pad, 'multimem': bool(use_mc),
+                   'epoch': torch.zeros(4, dtype=torch.int32, device=dev)}
 
     def reduce_gradients(self, grad: Optional[torch.Tensor] = None):
-        if self.world > 1:
+        """All-reduce of the flat gradient.  With the fused tail the reduction happens inside step(): nothing to do here
+        for the executor's own gradient buffer."""
+        if self.world > 1 and not (self.dp is not None and grad is None):
             dist.all_reduce(self.model.executor.flat_grad if grad is None else grad, op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self, grad: Optional[torch.Tensor] = None):
@@ -97,9 +147,15 @@ class FlatAdamTrainer:
         `grad`: a flat gradient other than the executor's own buffer (after `loss.backward()` through the autograd
         seam that is `model.executor.last_flat_grad`, of which every `p.grad` is a view)."""
         from .. import ops
+        scale = 1.0 / (self.world * self.accumulate)
+        if self.dp is not None and grad is None:
+            # reduce-scatter + Adam on this rank's slice + all-gather of the parameters, one kernel over peer memory
+            ops.dp_adam_step(self.dp['peers'], self.exp_avg, self.exp_avg_sq, self.step_dev, self.lr_dev, self.betas[0],
+                             self.betas[1], self.eps, scale, self.flat_param.numel(), self.dp['epoch'])
+            return
         g = self.model.executor.flat_grad if grad is None else grad
         ops.adam_step(self.flat_param, g, self.exp_avg, self.exp_avg_sq, self.step_dev,
-                      self.lr_dev, self.betas[0], self.betas[1], self.eps, 1.0 / (self.world * self.accumulate))
+                      self.lr_dev, self.betas[0], self.betas[1], self.eps, scale)
 
     def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
         res = self.model.fused_step(batch, laplacian)

@@ -462,6 +462,19 @@ class PinnExecutor:
         self._graphs: dict = {}
         self._seen: set = set()
 
+    def rebind_flat_grad(self, buf: Tensor) -> None:
+        """Move the flat gradient into caller-provided storage (the data-parallel trainer places it in symmetric memory so
+        that peers can read it).  Captured graphs hold the old address and are dropped."""
+        if buf.numel() != self.flat_grad.numel() or buf.dtype != torch.float32 or buf.device != self.flat_grad.device:
+            raise _lib.PcfdError('rebind_flat_grad: buffer does not match the flat gradient')
+        buf.copy_(self.flat_grad)
+        self.flat_grad = buf
+        off = 0
+        for p in self.params:
+            self.ctx.grads[id(p)] = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.reset_graphs()
+
     def reset_graphs(self) -> None:
         """Forget the captured step graphs (their kernels hold loss weights, scaler values and buffer addresses by
         value): the next call of a signature runs eagerly, the one after re-captures."""

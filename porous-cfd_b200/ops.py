@@ -533,6 +533,16 @@ def adam_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, 
                              lr.data_ptr(), beta1, beta2, eps, grad_scale, param.numel(), _stream()), 'pcfd_adam_step')
 
 
+def dp_adam_step(peers, exp_avg: Tensor, exp_avg_sq: Tensor, step: Tensor, lr: Tensor, beta1: float, beta2: float,
+                 eps: float, grad_scale: float, n: int, epoch: Tensor) -> None:
+    """Gradient reduce-scatter + Adam on this rank's slice + parameter all-gather in one kernel (pcfd_dp_adam_step);
+    `peers` is a _lib.DpPeers filled from the symmetric-memory handles (common/training.py)."""
+    lib = _lib.load()
+    _lib.launches += 2
+    check(lib.pcfd_dp_adam_step(C.byref(peers), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), step.data_ptr(), lr.data_ptr(),
+                                beta1, beta2, eps, grad_scale, n, epoch.data_ptr(), _stream()), 'pcfd_dp_adam_step')
+
+
 def zero_(t: Tensor) -> None:
     lib = _lib.load()
     _lib.launches += 1

@@ -41,14 +41,14 @@ def test_struct_layouts_match_header():
     import subprocess
     import tempfile
     from porous_cfd_b200 import _lib
-    src = '#include <stdio.h>\n#include "pcfd.h"\nint main(){printf("%zu %zu\\n", sizeof(pcfd_intrans_t), sizeof(pcfd_residual_params_t));return 0;}\n'
+    src = '#include <stdio.h>\n#include "pcfd.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(pcfd_intrans_t), sizeof(pcfd_residual_params_t), sizeof(pcfd_dp_peers_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, 'sz.c')
         open(c, 'w').write(src)
         exe = os.path.join(td, 'sz')
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
-        a, b = map(int, subprocess.check_output([exe]).split())
-    assert a == ctypes.sizeof(_lib.InTrans) and b == ctypes.sizeof(_lib.ResidualParams)
+        a, b, c_ = map(int, subprocess.check_output([exe]).split())
+    assert a == ctypes.sizeof(_lib.InTrans) and b == ctypes.sizeof(_lib.ResidualParams) and c_ == ctypes.sizeof(_lib.DpPeers)
 
 
 def test_no_cpu_fallback():
