@@ -593,7 +593,9 @@ def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int,
            'launches_per_step': (launches_per_micro + 1 + (1 if pipelined else 0)) * micro + 2 + (1 if micro > 1 else 0),
            'fallbacks': list(ops.FALLBACKS), 'b_micro': b_micro, 'micro': micro,
            'roofline': family_roofline(fam, prof_steps, env.peaks, engine_name) if rank == 0 else None,
-           'dev_batches': dev_batches, 'labels': labels, 'spec': spec, 'model': model, 'trainer': trainer}
+           'dev_batches': dev_batches, 'labels': labels, 'spec': spec, 'model': model, 'trainer': trainer,
+           'dp_tail': (None if world == 1 else 'nccl' if trainer.dp is None else ('multimem' if trainer.dp['multimem'] else 'p2p')),
+           'dp_error': int(trainer.dp['epoch'][2]) if trainer.dp is not None else 0}
     if e2e:
         out['e2e_value'] = pts_per_step * K / (ms_e2e_m / 1e3)
         out['e2e_ms_per_step'] = ms_e2e_m / K
@@ -722,8 +724,13 @@ def main():
                        'laplacian': args.laplacian, 'dropout': 'on', 'optimizer': 'fused Adam in the step',
                        'parallelism': f'dp{env.world}', 'cuda_graph': r['graph'],
                        'collective': ('none (N = 1)' if env.world == 1 else
-                                      'one NCCL all-reduce of the flat gradient + Adam, ' +
+                                      {'nccl': 'one NCCL all-reduce of the flat gradient + Adam, ',
+                                       'multimem': 'one kernel over NVSwitch multicast memory (pcfd_dp_adam_step: multimem.ld_reduce '
+                                                   'reduce-scatter, Adam on the rank\'s slice, multimem.st all-gather of the parameters), ',
+                                       'p2p': 'one kernel over NVLink peer memory (pcfd_dp_adam_step: peer loads, Adam on the rank\'s '
+                                              'slice, peer stores), '}[r['dp_tail']] +
                                       ('captured in the step graph' if r['tail_in_graph'] else 'launched behind the step graph')),
+                       'collective_barrier_timeouts': r['dp_error'],
                        'micro_batches_per_step': r['micro'],
                        'geometry': ('FPS / ball query of batch t+1 run as a parallel branch of step t (positions only; '
                                     'one batch worth per step)') if r['pipelined'] else 'inside the step',
