@@ -332,7 +332,10 @@ struct DwPlan {
 // rows per stage: the small value keeps wide tiles within shared memory, the large one amortises the
 // per-stage barrier round trips of narrow layers
 static inline int dw_rows_small(int cj) { return cj == 1 ? 16 : (cj == 4 ? 4 : 8); }
-static inline int dw_rows_large(int cj) { return cj == 1 ? 64 : (cj <= 4 ? 16 : 8); }
+// cj = 4: 16 rows never left room for 3 stages (96 KB per stage on the narrowest layer); with 8 rows the narrow layers
+// (3->64, 64->64, 128->4) run half as many ring iterations per CTA -- their time was the per-iteration latency chain
+// (ncu: 45 % of the samples in the transform warps' wait for the TMA barrier at 4 rows per stage)
+static inline int dw_rows_large(int cj) { return cj == 1 ? 64 : (cj == 4 ? 8 : (cj == 3 ? 16 : 8)); }
 
 // a waiter may only be one phase away from its barrier: the transform group of iteration `it` must also be
 // the group of iteration `it - stages`, so the number of groups in use divides the ring depth
@@ -571,7 +574,7 @@ extern "C" int pcfd_ws_jet_linear_bwd_dw_partials(const float* gzout, int64_t gz
   switch (cj) {
     case 1: PCFD_WS_DW(1, 16) PCFD_WS_DW(1, 64) break;
     case 3: PCFD_WS_DW(3, 8) PCFD_WS_DW(3, 16) break;
-    case 4: PCFD_WS_DW(4, 4) PCFD_WS_DW(4, 16) break;
+    case 4: PCFD_WS_DW(4, 4) PCFD_WS_DW(4, 8) break;
     case 5: PCFD_WS_DW(5, 8) break;
     case 7: PCFD_WS_DW(7, 8) break;
   }
