@@ -240,6 +240,44 @@ def geometry_cache_leg(model, trainer, dev_batches, labels, b: int, ni: int, ste
     return out
 
 
+def train_loop_leg(config: str, dev_batches, labels, b: int, ni: int, tmp_dir: str) -> dict:
+    """The reference-facing training loop itself (common.training.train: DataLoader + collate_fn on the host, pinned
+    upload one batch ahead, step replayed from a CUDA graph, Adam), on an in-memory dataset of this workload's geometries:
+    wall-clock points/s of whole epochs, host side included (reference loop: common/training.py:50-85)."""
+    from argparse import Namespace
+    from porous_cfd_b200.common.training import train
+    from porous_cfd_b200.dataset.foam_data import FoamData
+
+    class Mem(torch.utils.data.Dataset):
+        def __init__(self, items):
+            self.items = items
+
+        def __len__(self):
+            return len(self.items)
+
+        def __getitem__(self, i):
+            return self.items[i]
+
+    items = []
+    for d in dev_batches:
+        data = d.data.cpu()
+        dom = {k: v.cpu() for k, v in d.domain.items()}
+        items += [FoamData(data[i], labels, {k: v[i] for k, v in dom.items()}) for i in range(data.shape[0])]
+    model, _ = make_model(config, torch.device('cuda', torch.cuda.current_device()))
+    secs = []
+    args = Namespace(n_internal=ni, n_boundary=0, n_observations=0, batch_size=b, precision='32', epochs=6, logs_dir=tmp_dir,
+                     train_dir='', val_dir='', model=config, name='bench', checkpoint=None, loss_scaler='fixed',
+                     epoch_seconds=secs)
+    train(args, model, Mem(items), Mem([]))
+    steady = sorted(secs[2:])
+    sec = steady[len(steady) // 2]
+    steps = (len(items) + b - 1) // b
+    return {'epochs': len(secs), 'steps_per_epoch': steps, 'geometries': len(items), 'median_epoch_ms': 1e3 * sec,
+            'ms_per_step': 1e3 * sec / steps, 'points_per_s': len(items) * ni / sec,
+            'note': 'train(): host DataLoader (num_workers = 0) + collate_fn, pinned upload one batch ahead, CUDA-graph step, '
+                    'Adam; epochs 3-6 of 6 (the first two run eagerly / capture)'}
+
+
 def ingest_leg(dev_batches, labels, n_internal, dims, peaks):
     """SURVEY 8f rank 4, outside the timed step: collation of HBM-resident geometries (pcfd_gather_blocks) and the
     signed-distance feature (pcfd_sdf_feature) on this workload's shapes, CUDA events on the launching stream."""
@@ -707,6 +745,9 @@ def main():
     if env.world == 1:
         try:
             ingest = ingest_leg(r['dev_batches'], r['labels'], shape['n_internal'], r['spec']['dims'], env.peaks)
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                ingest['train_loop'] = train_loop_leg(config, r['dev_batches'], r['labels'], b_per_gpu, shape['n_internal'], td)
             if r['model'].executor.uses_geometry() and not args.no_graph:
                 ingest['geometry_cache'] = geometry_cache_leg(r['model'], r['trainer'], r['dev_batches'], r['labels'], b_per_gpu,
                                                               shape['n_internal'], r['steps'])

@@ -88,6 +88,7 @@ class FlatAdamTrainer:
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
             off += n
+        ex.reset_graphs()    # captured step graphs hold the parameters' old addresses
         if self.world > 1:   # identical replicas
             dist.broadcast(self.flat_param, 0, group=self.group)
         opt_cfg = model.configure_optimizers()[0][0]
@@ -157,8 +158,16 @@ class FlatAdamTrainer:
         ops.adam_step(self.flat_param, g, self.exp_avg, self.exp_avg_sq, self.step_dev,
                       self.lr_dev, self.betas[0], self.betas[1], self.eps, scale)
 
-    def train_step(self, batch: FoamData, laplacian: Optional[str] = None):
-        res = self.model.fused_step(batch, laplacian)
+    def train_step(self, batch: FoamData, laplacian: Optional[str] = None, graphed: bool = False):
+        """One optimizer step on `batch` (already on the device).  `graphed`: replay the fused step from the executor's
+        CUDA graph for this batch signature (first call eager, second captures) -- what `train` uses, because launching
+        the ~110 kernels of a step from Python takes longer than the GPU needs to run them."""
+        if graphed:
+            ex = self.model.executor
+            res = ex.graphed_step(batch.data, batch.labels, batch.domain, laplacian or self.model.laplacian,
+                                  geo=getattr(batch, 'geometry', None))
+        else:
+            res = self.model.fused_step(batch, laplacian)
         self.reduce_gradients()
         self.step()
         return res
@@ -271,13 +280,44 @@ def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
                 'global_step': global_step}
 
     history = []
+    graphed = bool(getattr(args, 'cuda_graph', True))
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def upload(host_batch):
+        """Host -> device copy of a collated batch on the copy stream (pinned by the DataLoader), one batch ahead of the
+        step that consumes it."""
+        with torch.cuda.stream(copy_stream):
+            dev = model.transfer_batch_to_device(host_batch, device)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev, ev
+
+    epoch_seconds = getattr(args, 'epoch_seconds', None)      # optional list: wall time of every training epoch (bench.py)
+    import time as _time
     for epoch in range(start_epoch, args.epochs):
         model.train()
         sampler.set_epoch(epoch)
         res = None
-        for batch in train_loader:
-            res = trainer.train_step(model.transfer_batch_to_device(batch, device))
+        if epoch_seconds is not None:
+            torch.cuda.synchronize()
+            t_epoch = _time.perf_counter()
+        it = iter(train_loader)
+        nxt = next(it, None)
+        pending = upload(nxt) if nxt is not None else None
+        while pending is not None:
+            batch, ev = pending
+            nxt = next(it, None)
+            pending = upload(nxt) if nxt is not None else None      # overlaps this step
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            batch.data.record_stream(cur)
+            for v in batch.domain.values():
+                v.record_stream(cur)
+            res = trainer.train_step(batch, graphed=graphed)
             global_step += 1
+        if epoch_seconds is not None:
+            torch.cuda.synchronize()
+            epoch_seconds.append(_time.perf_counter() - t_epoch)
         trainer.end_epoch()
         if rank == 0 and res is not None:
             history.append(float(res.loss))
