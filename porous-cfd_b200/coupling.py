@@ -155,7 +155,7 @@ def forward(ex, data: Tensor, labels: dict, int_ids: Tensor, zs_int, saved: dict
     ii = torch.arange(d + 1, device=data.device)[:, None, None].expand_as(contrib)
     kk = (1 + torch.arange(d, device=data.device))[None, :, None].expand_as(contrib)
     rr = st.rows[None, None, :].expand_as(contrib)
-    y.t.index_put_((kk, rr, ii), contrib, accumulate=True)
+    _scatter_add(y.t, (y.t.stride(0), y.t.stride(1), 1), (kk, rr, ii), contrib)
 
     # ---- the Laplacian as written (get_laplacian(points, U), models/model_base.py:195): lap[n, i, j] =
     #      dU_j(point i)/dx_j(point n) = delta(n, i) dU_j(i)/dx_j |_g + sum_{c: a(c)=n} s^(i)_jc H_cj(n).
@@ -178,12 +178,11 @@ def forward(ex, data: Tensor, labels: dict, int_ids: Tensor, zs_int, saved: dict
     st.s1 = s1                                                                   # [i, j, B*G]
     vx = torch.zeros((b * ni, d), dtype=torch.float32, device=data.device)
     add = (st.s1 * (st.w[None, :, None] * hk[None, :, :])).sum(1)               # [i, B*G]: sum_j w_j s^(i)_jc H_cj
-    vx.index_put_((st.rows[None, :].expand_as(add), torch.arange(d, device=data.device)[:, None].expand_as(add)), add,
-                  accumulate=True)
+    _scatter_add(vx, (d, 1), (st.rows[None, :].expand_as(add), torch.arange(d, device=data.device)[:, None].expand_as(add)), add)
     # minus the coupling part of the diagonal the kernel reads at rows n = i < D:  sum_j w_j C[n, j, j]
     diag = torch.stack([contrib[j, j] for j in range(d)])                         # [j, B*G] = C[a(c), j, j] per (b, c)
     corr = -(st.w[:, None] * diag).sum(0) * (st.local_row < d).float() * st.mask  # [B*G]
-    vx.index_put_((st.rows, st.local_row.clamp(max=d - 1)), corr, accumulate=True)
+    _scatter_add(vx, (d, 1), (st.rows, st.local_row.clamp(max=d - 1)), corr)
     st.visc_extra = vx
     st.gvisc = torch.empty_like(vx)
     return st
@@ -270,11 +269,22 @@ def backward(ex, st: Coupling, data: Tensor, int_ids: Tensor, zs_int, gy_int: Je
     gh = Jet.empty(zh.cj, zh.rows, zh.width, dev)
     ops.zero_(gh.t)
     g0 = (mu * f2 * st.hz[1:1 + d]).sum(0) * st.mask
-    gh.t.index_put_((torch.zeros(bg, dtype=torch.long, device=dev), st.rows, st.cols), g0, accumulate=True)
+    _scatter_add(gh.t, (gh.t.stride(0), gh.t.stride(1), 1), (torch.zeros(bg, dtype=torch.long, device=dev), st.rows, st.cols), g0)
     kk = (1 + torch.arange(d, device=dev))[:, None].expand(d, bg)
-    gh.t.index_put_((kk, st.rows[None].expand(d, bg), st.cols[None].expand(d, bg)), mu * f1, accumulate=True)
+    _scatter_add(gh.t, (gh.t.stride(0), gh.t.stride(1), 1), (kk, st.rows[None].expand(d, bg), st.cols[None].expand(d, bg)), mu * f1)
     gin = chain_backward(ctx, glayers, st.zs_h, gh, ni, need_input_grad=True)
     chain_backward(ctx, plan['local_layers'], zs_int[:nl + 1], Jet(gin.t, lw), ni, salt_base=100)
+
+
+def _scatter_add(target: Tensor, strides, index_parts, values: Tensor) -> None:
+    """target[i0, i1, ...] += values at broadcast index tensors `index_parts`, as ONE atomic-add kernel on the flattened
+    target (index_put_(accumulate=True) sorts the indices first: a radix sort, a bounds reduction and an assert launch per
+    call).  `strides`: element strides of the contiguous target."""
+    lin = None
+    for st_, ix in zip(strides, index_parts):
+        term = ix * st_
+        lin = term if lin is None else lin + term
+    target.view(-1).index_add_(0, lin.reshape(-1), values.reshape(-1))
 
 
 def _pad4(t: Tensor) -> Tensor:
