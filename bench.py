@@ -658,7 +658,9 @@ def extra_configs(env: Env) -> list:
         plan.append(dict(config=4, name='windbreaks_pigano_pp', shape=WORKLOADS['windbreaks_pigano_pp']['shape'], per_gpu=b,
                          micro_geoms=8, steps=10, scaling='weak'))
     # config 5: manufactured PIPN++ sweep, 256 geometries in total; NB = NI / 4, no observations
-    for ni, mg, st in ((4096, 64, 10), (65536, 4, 3)) + (((262144, 1, 2),) if world >= 8 else ()):
+    # micro-batch sizes: as many geometries per launch as fit comfortably in HBM (~35 GB of jets at 1 M collocation points):
+    # FPS runs one CTA per geometry, so few geometries per micro-batch leave it as the critical path
+    for ni, mg, st in ((4096, 64, 10), (65536, 16, 3)) + (((262144, 4, 2),) if world >= 8 else ()):
         plan.append(dict(config=5, name='manufactured_pipn_pp', shape=dict(n_internal=ni, n_boundary=ni // 4, n_obs=0),
                          total=256, micro_geoms=mg, steps=st, scaling='strong'))
     out = []
