@@ -575,9 +575,9 @@ class PinnExecutor:
 
     def _encode_pipn(self, data, labels, pts_int_ids, pts_bnd_ids, points):
         """Vanilla PIPN global feature (models/modules.py:71-82): local MLP on every point, concat with
-        [boundaryId, sdf], global MLP, max over points.  Value path only: the dependence of the pooled
-        feature on the autograd points (max-pool coupling) is NOT carried in
-        the tangents."""
+        [boundaryId, sdf], global MLP, max over points.  This is the VALUE path; the dependence of the pooled
+        feature on the autograd points (max-pool coupling) enters the step through
+        coupling.py (`laplacian='reference'`: exact; `'true'`: per-point terms only)."""
         plan, ctx = self.plan, self.ctx
         b, n_rows, f = data.shape
         d = plan['dims']
