@@ -25,8 +25,6 @@ second jet pass (direction channels instead of spatial ones) followed by the ord
 """
 from __future__ import annotations
 
-import os
-
 from typing import Optional
 
 import torch
@@ -77,41 +75,6 @@ def decoder_vjp(ex, zs, rows_per_geom: int, gz: Jet, salt_base: int, n_geom: int
     if keep_rows is not None:
         return out, gz.t[0].index_select(0, keep_rows)
     return out
-
-
-def decoder_vjp_all(ex, zs, rows_per_geom: int, n_dirs: int, n_out_width: int, salt_base: int, n_geom: int,
-                    keep_rows: Tensor):
-    """The D+1 value-only reverse sweeps of decoder_vjp (cotangent = unit vector of output i, i < n_dirs) in ONE pass:
-    the sweeps share the pre-activations, so they ride as the channels of a jet whose tangent planes are ZERO -- the reverse
-    activation jet then reduces to g_c <- f'(z0) g_c on every channel, which is exactly a value-only sweep per channel (same
-    dropout mask: it is keyed on (row, column)).  One cj = D+1 kernel per layer instead of D+1 value-only kernels on a
-    sixth of the rows each.  Returns ([per direction] column sums per geometry [n_geom, ld], [per direction] rows kept)."""
-    from .engine import _tin
-    ctx, layers = ex.ctx, ex.plan['point_layers']
-    ci = _concat_index(layers)
-    rows = zs[-1].rows
-    dev = zs[-1].t.device
-    gz = Jet.empty(n_dirs, rows, n_out_width, dev)
-    ops.zero_(gz.t)
-    for i in range(n_dirs):
-        gz.t[i, :, i] = 1.0
-    for li in range(len(layers) - 1, ci, -1):
-        L = layers[li]
-        zq = Jet.empty(n_dirs, rows, zs[li].width, dev)
-        ops.zero_(zq.t)
-        ops.gather_cols(zs[li].t[0], 1, rows, zs[li].ld, None, 0, rows, list(range(zs[li].width)), zq.t[0], zq.ld, rows)
-        gz = ops.jet_linear_bwd_dx(gz, L.weight, L.col_lo, zq, _tin(ctx, L, None, salt_base + li), None, rows_per_geom,
-                                   L.k, L.n)
-    Lc = layers[ci]
-    outs, kept = [], []
-    for i in range(n_dirs):
-        out = torch.zeros((n_geom, ops.round4(Lc.n)), dtype=torch.float32, device=dev)
-        gi = Jet(gz.t[i:i + 1], gz.width)
-        ops.jet_linear_bwd_dw(gi, _plane0(zs[ci]), None, None, 0, None, out, rows_per_geom, Lc.k, Lc.n,
-                              ctx.need_workspace(ops.dw_workspace_bytes(1, rows, rows_per_geom, Lc.k, Lc.n)))
-        outs.append(out)
-        kept.append(gz.t[i].index_select(0, keep_rows))
-    return outs, kept
 
 
 class Coupling:
@@ -173,17 +136,11 @@ def forward(ex, data: Tensor, labels: dict, int_ids: Tensor, zs_int, saved: dict
     geom_first = torch.arange(b, device=data.device) * ni
     first_rows = (geom_first[None, :] + torch.arange(d, device=data.device)[:, None]).reshape(-1)   # (point i, geometry b)
     single = []       # per output j: cotangent of the concat pre-activation at the first D points of every geometry
-    batched = os.environ.get('PCFD_COUPLING_BATCHED', '1') != '0'
-    if batched:
-        gcv_all, first_all = decoder_vjp_all(ex, zs_int, ni, d + 1, y.width, 100, b, first_rows)
     for i in range(d + 1):
-        if batched:
-            gcv, r_first = gcv_all[i], first_all[i]
-        else:           # one value-only sweep per output (the independent form the batched pass is tested against)
-            gz = Jet.empty(1, y.rows, y.width, data.device)
-            ops.zero_(gz.t)
-            gz.t[0, :, i] = 1.0
-            gcv, r_first = decoder_vjp(ex, zs_int, ni, gz, 100, b, first_rows)
+        gz = Jet.empty(1, y.rows, y.width, data.device)
+        ops.zero_(gz.t)
+        gz.t[0, :, i] = 1.0
+        gcv, r_first = decoder_vjp(ex, zs_int, ni, gz, 100, b, first_rows)
         if i < d:
             single.append(r_first)      # the decoder is per-point: row (b, i) of this sweep IS dU_i... /dp at that single point
         st.gcv.append(gcv)

@@ -544,23 +544,3 @@ def test_one_launch_residual_equals_the_four_launch_form(name, mode):
     a, b = outs[True], outs[False]
     assert float((a[0] - b[0]).abs().max()) <= 2e-6 * float(b[0].abs().max())
     assert rel_l2(a[1].double().cpu(), b[1].double().cpu()) < 2e-6
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize('name', COUPLED)
-def test_coupling_batched_sweeps_equal_per_output_sweeps(name, monkeypatch):
-    """The D+1 value-only decoder sweeps of the vanilla-PIPN coupling as ONE jet pass with zero tangent planes
-    (coupling.decoder_vjp_all) against one sweep per output: same losses, same gradients."""
-    spec = synthetic.model_spec(name)
-    _, _, params, _ = load_fixture(name)
-    labels = synthetic.build_labels(spec['layout'])
-    data, _, domain = synthetic.make_batch(spec['layout'], seed=31, **TINY_SHAPE)
-    outs = {}
-    for flag in ('1', '0'):
-        monkeypatch.setenv('PCFD_COUPLING_BATCHED', flag)
-        model = cuda_model(spec, params)
-        res, grads = run_step(model, data, labels, domain, 'reference')
-        outs[flag] = (res.losses.clone(), grads)
-    keys = list(outs['1'][1])
-    assert max_rel(outs['1'][0], outs['0'][0]) < 1e-6
-    assert rel_l2(flat(outs['1'][1], keys), flat(outs['0'][1], keys)) < 1e-6
