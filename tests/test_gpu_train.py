@@ -84,6 +84,33 @@ def test_resume_continues_exactly_where_the_run_stopped(tmp_path):
     assert rel_l2(c['trainer']['exp_avg'].double(), a['trainer']['exp_avg'].double()) < 1e-4
 
 
+def test_train_with_relobralo_resumes_the_scaler_state(tmp_path):
+    """train() with the adaptive scaler: the batch size reaches the scaler (the reference reads it from the trainer's
+    DataLoader), the step counter follows the global step, and a resumed run keeps the restored init / previous losses
+    (reference: RelobraloScaler keys on model.global_step, models/losses.py:93-124)."""
+    from porous_cfd_b200.common.training import train
+    from porous_cfd_b200.models.losses import RelobraloScaler
+    model, spec = _model('tiny_pipn_pp')
+    n_terms = 2 * spec['dims'] + 2 + spec['dims'] + 1
+    model.loss_scaler = RelobraloScaler(n_terms, alpha=0.9, beta=1.0)
+    ds = _SyntheticSet(spec['layout'], 8, 40, 24, 10)
+    val = _SyntheticSet(spec['layout'], 2, 40, 24, 10, seed=9)
+    hist = train(_args(tmp_path / 'a', epochs=2, loss_scaler='relobralo'), model, ds, val)
+    assert all(torch.isfinite(torch.tensor(hist)))
+    assert model.loss_scaler.batch_size == 4
+    step, _ = model.loss_scaler.device_state(torch.device('cuda', 0))
+    assert int(step) == 4                                   # 2 epochs x 2 steps
+    init = model.loss_scaler.init_losses.clone()
+    assert float(init.abs().sum()) > 0
+    ck = tmp_path / 'a' / 'lightning_logs' / 'run' / 'model.ckpt'
+    again, _ = _model('tiny_pipn_pp', seed=11)
+    again.loss_scaler = RelobraloScaler(n_terms, alpha=0.9, beta=1.0)
+    train(_args(tmp_path / 'b', epochs=3, loss_scaler='relobralo', checkpoint=str(ck)), again, ds, val)
+    assert torch.equal(again.loss_scaler.init_losses.cpu(), init.cpu())       # not re-initialised by the first resumed step
+    step2, _ = again.loss_scaler.device_state(torch.device('cuda', 0))
+    assert int(step2) == 6
+
+
 def test_accumulated_micro_batches_equal_one_batch():
     from porous_cfd_b200 import synthetic
     from porous_cfd_b200.dataset.foam_data import FoamData
