@@ -20,8 +20,8 @@ int pcfd_thin_jet_linear_fwd(const float*, int64_t, int32_t, const pcfd_intrans_
                              void*);
 int pcfd_thin_dx_kind(const pcfd_intrans_t*, const float*, int32_t, int64_t, int32_t, int32_t);
 int pcfd_thin_jet_linear_bwd_dx(const float*, int64_t, int32_t, const float*, int32_t, const float*, int64_t, int32_t,
-                                const pcfd_intrans_t*, float*, int64_t, int32_t, int32_t, int64_t, int64_t, int32_t, int32_t,
-                                void*);
+                                const pcfd_intrans_t*, float*, int64_t, int32_t, float*, int32_t, int32_t, int64_t, int64_t,
+                                int32_t, int32_t, void*);
 int pcfd_small_rows_supported_dw(const pcfd_intrans_t*, int32_t, int64_t, int32_t, int32_t);
 int pcfd_small_rows_bwd_dw(const float*, int32_t, const float*, int32_t, float*, int32_t, float*, float*, int32_t, int64_t,
                            int64_t, int32_t, int32_t, void*);
@@ -98,8 +98,8 @@ extern "C" int pcfd_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int3
   int rc = ensure_arch();
   if (rc) return rc;
   if (pcfd_thin_dx_kind(tin, gescale, cj, rows, k, n) >= 0)
-    return pcfd_thin_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin, cj,
-                                       rows, rows_per_geom, k, n, stream);
+    return pcfd_thin_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
+                                       gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);
   if (pcfd_ws_supported_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, gzin, gzin_ps, ldgzin, cj, rows, k, n))
     return pcfd_ws_jet_linear_bwd_dx(gzout, gzout_ps, ldgzout, w, ldw, zin, zin_ps, ldzin, tin, gzin, gzin_ps, ldgzin,
                                      gescale, ldgescale, cj, rows, rows_per_geom, k, n, stream);

@@ -206,6 +206,93 @@ __global__ void __launch_bounds__(256) thin_n_dx_kernel(ThinDxArgs a) {
   }
 }
 
+// thin_n dX with the branch-scaling gradient (PI-GANO reduction layer, models/pi_gano/pi_gano.py:66-69 through the
+// operators of models/modules.py:232-245): same arithmetic per (row, 4 input columns), but a thread keeps its column chunk
+// and walks the rows of ONE geometry, so d loss / d escale[geometry][column] is summed in registers and leaves as one atomic
+// per (thread, column) instead of one per element.  Block = kchunks column chunks x (256 / kchunks) row lanes.
+template <int CJ>
+__global__ void __launch_bounds__(256) thin_n_dx_ge_kernel(ThinDxArgs a, float* gescale, int ldgescale, int rows_block) {
+  extern __shared__ float wsm[];                       // [8][k4]
+  const int k4 = (a.k + 3) & ~3;
+  for (int i = threadIdx.x; i < 8 * k4; i += 256) {
+    const int j = i / k4, kk = i - j * k4;
+    wsm[i] = (j < a.n && kk < a.k) ? __ldg(a.w + (int64_t)j * a.ldw + kk) : 0.0f;
+  }
+  __syncthreads();
+  const uint64_t seed = a.tin.seed_dev ? *a.tin.seed_dev : 0ULL;
+  const int kchunks = k4 >> 2;
+  const int lanes = 256 / kchunks;
+  const int chunk = (int)threadIdx.x % kchunks, lane = (int)threadIdx.x / kchunks;
+  if (lane >= lanes) return;
+  const int64_t blocks_per_geom = (a.rows_per_geom + rows_block - 1) / rows_block;
+  const int64_t geom = (int64_t)blockIdx.x / blocks_per_geom;
+  const int64_t rb = (int64_t)blockIdx.x - geom * blocks_per_geom;
+  const int64_t r_lo = geom * a.rows_per_geom + rb * rows_block;
+  int64_t r_hi = r_lo + rows_block;
+  if (r_hi > (geom + 1) * a.rows_per_geom) r_hi = (geom + 1) * a.rows_per_geom;
+  if (r_hi > a.rows) r_hi = a.rows;
+  const int col0 = chunk * 4;
+  float ge_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t row = r_lo + lane; row < r_hi; row += lanes) {
+    float g[CJ][4];
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) { g[c][0] = 0.f; g[c][1] = 0.f; g[c][2] = 0.f; g[c][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < a.n) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wsm + j * k4 + col0);
+#pragma unroll
+        for (int c = 0; c < CJ; ++c) {
+          const float gz = __ldg(a.gzout + c * a.gzout_ps + row * a.ldgzout + j);
+          g[c][0] = fmaf(gz, w4.x, g[c][0]); g[c][1] = fmaf(gz, w4.y, g[c][1]);
+          g[c][2] = fmaf(gz, w4.z, g[c][2]); g[c][3] = fmaf(gz, w4.w, g[c][3]);
+        }
+      }
+    }
+    if (col0 < a.tin.act_cols) {
+      float z[CJ][4];
+#pragma unroll
+      for (int c = 0; c < CJ; ++c) {
+        const float* p = a.zin + c * a.zin_ps + row * a.ldzin + col0;
+        if (a.vec_in && col0 + 4 <= a.k) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+          z[c][0] = x.x; z[c][1] = x.y; z[c][2] = x.z; z[c][3] = x.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[c][e] = col0 + e < a.k ? __ldg(p + e) : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (col0 + e < a.tin.act_cols) {
+          float zz[CJ], gg[CJ];
+#pragma unroll
+          for (int c = 0; c < CJ; ++c) { zz[c] = z[c][e]; gg[c] = g[c][e]; }
+          float m;
+          const float s = in_scale(a.tin, seed, row, geom, col0 + e, m);
+          ge_acc[e] += jet_act_bwd<CJ>(a.tin.act, s, m, zz, gg);
+#pragma unroll
+          for (int c = 0; c < CJ; ++c) g[c][e] = gg[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CJ; ++c) {
+      float* p = a.gzin + c * a.gzin_ps + row * a.ldgzin + col0;
+      if (a.vec_out && col0 + 4 <= a.ldgzin) {
+        *reinterpret_cast<float4*>(p) = make_float4(g[c][0], g[c][1], g[c][2], g[c][3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col0 + e < a.k) p[e] = g[c][e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (col0 + e < a.k && ge_acc[e] != 0.0f) atomicAdd(gescale + geom * ldgescale + col0 + e, ge_acc[e]);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // thin_k forward: one thread per (row, 4 output columns)
 // ---------------------------------------------------------------------------------------------------------------
@@ -389,9 +476,11 @@ extern "C" int pcfd_thin_jet_linear_fwd(const float* zin, int64_t zin_ps, int32_
   return PCFD_OK;
 }
 
+// kind 3: thin_n with the branch-scaling gradient (thin_n_dx_ge_kernel): needs one thread per column chunk in a block
 extern "C" int pcfd_thin_dx_kind(const pcfd_intrans_t* tin, const float* gescale, int32_t cj, int64_t rows, int32_t k,
                                  int32_t n) {
-  if (!valid_cj(cj) || gescale != nullptr || rows >= ((int64_t)1 << 31) / 512) return -1;
+  if (!valid_cj(cj) || rows >= ((int64_t)1 << 31) / 512) return -1;
+  if (gescale != nullptr) return (n <= 8 && k <= 1024 && tin != nullptr && tin->escale != nullptr) ? 3 : -1;
   if (rows <= 32 && cj == 1 && tin == nullptr) return 2;
   if (n <= 8 && k <= 1536) return 0;
   return -1;
@@ -400,10 +489,11 @@ extern "C" int pcfd_thin_dx_kind(const pcfd_intrans_t* tin, const float* gescale
 extern "C" int pcfd_thin_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps, int32_t ldgzout, const float* w,
                                            int32_t ldw, const float* zin, int64_t zin_ps, int32_t ldzin,
                                            const pcfd_intrans_t* tin, float* gzin, int64_t gzin_ps, int32_t ldgzin,
+                                           float* gescale, int32_t ldgescale,
                                            int32_t cj, int64_t rows, int64_t rows_per_geom, int32_t k, int32_t n,
                                            void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int kind = pcfd_thin_dx_kind(tin, nullptr, cj, rows, k, n);
+  const int kind = pcfd_thin_dx_kind(tin, gescale, cj, rows, k, n);
   if (kind < 0) return PCFD_ERR_ARG;
   if (kind == 2) {
     small_rows_kernel<true><<<(k + 7) / 8, 256, 0, st>>>(gzout, ldgzout, w, ldw, nullptr, nullptr, 0, gzin, ldgzin,
@@ -417,6 +507,20 @@ extern "C" int pcfd_thin_jet_linear_bwd_dx(const float* gzout, int64_t gzout_ps,
   a.vec_out = al16(gzin) && ldgzin % 4 == 0 && (cj == 1 || gzin_ps % 4 == 0);
   const int k4 = (k + 3) & ~3;
   const int smem = 8 * k4 * 4;
+  if (kind == 3) {
+    if (rows_per_geom <= 0 || rows % rows_per_geom != 0) return PCFD_ERR_ARG;
+    // rows of a geometry in blocks of (row lanes x 32): 32 rows per thread amortise the atomics of the scaling gradient
+    const int lanes = 256 / (k4 / 4);
+    int rows_block = lanes * 32;
+    const int64_t n_geom = rows / rows_per_geom;
+    const int64_t blocks_per_geom = (rows_per_geom + rows_block - 1) / rows_block;
+    const unsigned gridg = (unsigned)(n_geom * blocks_per_geom);
+#define PCFD_THIN_GE(CJ_) thin_n_dx_ge_kernel<CJ_><<<gridg, 256, smem, st>>>(a, gescale, ldgescale, rows_block); break;
+    switch (cj) { case 1: PCFD_THIN_GE(1) case 3: PCFD_THIN_GE(3) case 4: PCFD_THIN_GE(4) case 5: PCFD_THIN_GE(5) case 7: PCFD_THIN_GE(7) }
+#undef PCFD_THIN_GE
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
   const int grid = grid_for(rows * (k4 / 4), 256);
 #define PCFD_THIN(CJ_) thin_n_dx_kernel<CJ_><<<grid, 256, smem, st>>>(a); break;
   switch (cj) { case 1: PCFD_THIN(1) case 3: PCFD_THIN(3) case 4: PCFD_THIN(4) case 5: PCFD_THIN(5) case 7: PCFD_THIN(7) }
