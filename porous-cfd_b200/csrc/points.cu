@@ -392,6 +392,22 @@ __global__ void gather_cols_kernel(const float* __restrict__ data, int64_t n_row
       __ldg(data + (g * n_rows + src_row) * f + (identity_cols ? c : cols.c[c]));
 }
 
+// the same gather for consecutive columns of 16-byte aligned rows (the row gathers of the compacted max-pool backward,
+// jets copied between buffers): one thread per (row, 4 columns), 16-byte loads and stores
+__global__ void __launch_bounds__(256) gather_rows_vec_kernel(const float* __restrict__ data, int64_t n_rows, int f,
+                                                              const int64_t* __restrict__ row_ids, int64_t first_row, int64_t n_sel,
+                                                              int chunks, int64_t total, float* __restrict__ out, int ldout,
+                                                              int64_t out_rows_per_geom, int64_t out_row_offset, int out_col_offset) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % chunks) * 4;
+  const int64_t gi = t / chunks;
+  const int64_t i = gi % n_sel, g = gi / n_sel;
+  const int64_t src_row = row_ids != nullptr ? __ldg(row_ids + g * n_sel + i) : first_row + i;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(data + (g * n_rows + src_row) * f + c));
+  *reinterpret_cast<float4*>(out + (g * out_rows_per_geom + out_row_offset + i) * ldout + out_col_offset + c) = v;
+}
+
 __global__ void seed_jet_kernel(const float* __restrict__ data, int64_t n_rows, int f,
                                 const int64_t* __restrict__ row_ids, int64_t n_sel, ColList cols, int dims, int cj,
                                 int64_t total, float* __restrict__ z, int64_t ps, int ldz) {
@@ -617,6 +633,16 @@ extern "C" int pcfd_gather_cols(const float* data, int32_t n_geom, int64_t n_row
       if (cols_host[i] < 0 || cols_host[i] >= f) return PCFD_ERR_ARG;
       cl.c[i] = cols_host[i];
     }
+  // identity columns in whole 16-byte chunks of aligned rows: the vector form
+  if (cols_host == nullptr && n_cols % 4 == 0 && n_cols >= 4 && f % 4 == 0 && ldout % 4 == 0 && out_col_offset % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(data) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int chunks = n_cols / 4;
+    const int64_t total4 = (int64_t)n_geom * n_sel * chunks;
+    gather_rows_vec_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        data, n_rows, f, row_ids, first_row, n_sel, chunks, total4, out, ldout, out_rows_per_geom, out_row_offset, out_col_offset);
+    PCFD_CHECK_LAUNCH();
+    return PCFD_OK;
+  }
   const int64_t total = (int64_t)n_geom * n_sel * n_cols;
   gather_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       data, n_rows, f, row_ids, first_row, n_sel, cl, cols_host == nullptr ? 1 : 0, n_cols, total, out, ldout,
