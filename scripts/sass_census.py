@@ -9,7 +9,7 @@ import sys
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(R, 'porous-cfd_b200', 'libpcfd_sm100.so')
-KEYS = ['UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM', 'STTM', 'UTCBAR', 'MUFU', 'FFMA', 'HMMA']
+KEYS = ['UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM', 'STTM', 'UTCBAR', 'LDGMC', 'MUFU', 'FFMA', 'HMMA']
 
 
 def main():
@@ -40,7 +40,8 @@ def main():
     print('# SASS census of `porous-cfd_b200/libpcfd_sm100.so` (sm_100a)\n')
     print('`cuobjdump -sass` of the built library, instruction counts per kernel (template instances summed). '
           '`UTCHMMA` = tcgen05.mma, `UTMALDG`/`UTMASTG` = TMA load / store, `LDTM`/`STTM` = tcgen05.ld / st, '
-          '`UTCBAR` = tcgen05.commit. No `HMMA` (legacy mma.sync) anywhere.\n')
+          '`UTCBAR` = tcgen05.commit, `LDGMC` = multimem.ld_reduce (the NVSwitch adds the ranks\' copies in flight; multimem.st compiles '
+          'to `STG.E.128.STRONG.SYS` on the multicast address). No `HMMA` (legacy mma.sync) anywhere.\n')
     print('| kernel | instances | instructions | ' + ' | '.join(KEYS) + ' |')
     print('|---|---:|---:|' + '---:|' * len(KEYS))
     fam = collections.OrderedDict()
