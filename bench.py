@@ -263,19 +263,22 @@ def train_loop_leg(config: str, dev_batches, labels, b: int, ni: int, tmp_dir: s
         data = d.data.cpu()
         dom = {k: v.cpu() for k, v in d.domain.items()}
         items += [FoamData(data[i], labels, {k: v[i] for k, v in dom.items()}) for i in range(data.shape[0])]
-    model, _ = make_model(config, torch.device('cuda', torch.cuda.current_device()))
-    secs = []
-    args = Namespace(n_internal=ni, n_boundary=0, n_observations=0, batch_size=b, precision='32', epochs=6, logs_dir=tmp_dir,
-                     train_dir='', val_dir='', model=config, name='bench', checkpoint=None, loss_scaler='fixed',
-                     epoch_seconds=secs)
-    train(args, model, Mem(items), Mem([]))
-    steady = sorted(secs[2:])
-    sec = steady[len(steady) // 2]
     steps = (len(items) + b - 1) // b
-    return {'epochs': len(secs), 'steps_per_epoch': steps, 'geometries': len(items), 'median_epoch_ms': 1e3 * sec,
-            'ms_per_step': 1e3 * sec / steps, 'points_per_s': len(items) * ni / sec,
-            'note': 'train(): host DataLoader (num_workers = 0) + collate_fn, pinned upload one batch ahead, CUDA-graph step, '
-                    'Adam; epochs 3-6 of 6 (the first two run eagerly / capture)'}
+    out = {'epochs': 6, 'steps_per_epoch': steps, 'geometries': len(items),
+           'note': 'train(): CUDA-graph step + Adam; epochs 3-6 of 6 (the first two run eagerly / capture).  host_loader: host '
+                   'DataLoader (num_workers = 0) + collate_fn, pinned upload one batch ahead; device_dataset: the training set '
+                   'resident in HBM, collation on the device (args.device_dataset = True)'}
+    for mode, extra in (('host_loader', {}), ('device_dataset', {'device_dataset': True})):
+        model, _ = make_model(config, torch.device('cuda', torch.cuda.current_device()))
+        secs = []
+        args = Namespace(n_internal=ni, n_boundary=0, n_observations=0, batch_size=b, precision='32', epochs=6,
+                         logs_dir=os.path.join(tmp_dir, mode), train_dir='', val_dir='', model=config, name='bench', checkpoint=None,
+                         loss_scaler='fixed', epoch_seconds=secs, **extra)
+        train(args, model, Mem(items), Mem([]))
+        steady = sorted(secs[2:])
+        sec = steady[len(steady) // 2]
+        out[mode] = {'median_epoch_ms': 1e3 * sec, 'ms_per_step': 1e3 * sec / steps, 'points_per_s': len(items) * ni / sec}
+    return out
 
 
 def ingest_leg(dev_batches, labels, n_internal, dims, peaks):

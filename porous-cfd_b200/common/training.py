@@ -294,6 +294,16 @@ def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
 
     epoch_seconds = getattr(args, 'epoch_seconds', None)      # optional list: wall time of every training epoch (bench.py)
     import time as _time
+    # Optional: keep the whole training set in HBM and collate on the device (DeviceFoamDataset) --
+    # `args.device_dataset = True`; with `args.geometry_cache = True` the batches also carry their cached FPS / ball-query
+    # results (exact with this build's fixed FPS start).  The sample order is the same epoch_indices rule.
+    device_data = None
+    if getattr(args, 'device_dataset', False):
+        from ..dataset.device_dataset import DeviceFoamDataset
+        device_data = DeviceFoamDataset.from_samples([train_data[i] for i in range(len(train_data))], device=device)
+        if getattr(args, 'geometry_cache', False) and model.executor.uses_geometry():
+            device_data.build_geometry_cache(model)
+
     for epoch in range(start_epoch, args.epochs):
         model.train()
         sampler.set_epoch(epoch)
@@ -301,9 +311,16 @@ def train(args: Namespace, model, train_data: Dataset, val_data: Dataset):
         if epoch_seconds is not None:
             torch.cuda.synchronize()
             t_epoch = _time.perf_counter()
-        it = iter(train_loader)
-        nxt = next(it, None)
-        pending = upload(nxt) if nxt is not None else None
+        if device_data is not None:
+            order = epoch_indices(len(train_data), epoch, rank, world)
+            for lo in range(0, len(order), args.batch_size):
+                res = trainer.train_step(device_data.batch(order[lo:lo + args.batch_size]), graphed=graphed)
+                global_step += 1
+            it, pending = None, None
+        else:
+            it = iter(train_loader)
+            nxt = next(it, None)
+            pending = upload(nxt) if nxt is not None else None
         while pending is not None:
             batch, ev = pending
             nxt = next(it, None)

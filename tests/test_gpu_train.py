@@ -111,6 +111,24 @@ def test_train_with_relobralo_resumes_the_scaler_state(tmp_path):
     assert int(step2) == 6
 
 
+@pytest.mark.parametrize('name', ['tiny_pigano', 'tiny_pipn_pp'])
+def test_train_from_an_hbm_resident_dataset_equals_the_host_loader(tmp_path, name):
+    """train(args.device_dataset=True [, geometry_cache=True]): same sample order, same steps, same weights as the host
+    DataLoader path (collation on the device replaces DataLoader + collate_fn + upload)."""
+    from porous_cfd_b200.common.training import train
+    _, spec = _model(name)
+    ds = _SyntheticSet(spec['layout'], 10, 40, 24, 10)
+    val = _SyntheticSet(spec['layout'], 2, 40, 24, 10, seed=9)
+    host, _ = _model(name)
+    train(_args(tmp_path / 'h', epochs=2), host, ds, val)
+    dev, _ = _model(name)
+    train(_args(tmp_path / 'd', epochs=2, device_dataset=True, geometry_cache=True), dev, ds, val)
+    a = torch.load(tmp_path / 'h' / 'lightning_logs' / 'run' / 'model.ckpt', map_location='cpu')['state_dict']
+    b = torch.load(tmp_path / 'd' / 'lightning_logs' / 'run' / 'model.ckpt', map_location='cpu')['state_dict']
+    for k in a:
+        assert rel_l2(b[k].double(), a[k].double()) < 1e-4, k
+
+
 def test_accumulated_micro_batches_equal_one_batch():
     from porous_cfd_b200 import synthetic
     from porous_cfd_b200.dataset.foam_data import FoamData
