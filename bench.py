@@ -478,7 +478,7 @@ def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int,
                     geo_side = torch.cuda.Stream()
                     torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                     if pipelined:
                         cap = torch.cuda.current_stream()
                         geo_side.wait_stream(cap)

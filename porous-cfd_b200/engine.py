@@ -371,7 +371,10 @@ class GraphedStep:
             self.geo_side = torch.cuda.Stream(device=data.device)
         torch.cuda.current_stream().synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: only this thread's calls are checked against the capture.  A DataLoader's pin-memory thread (train()'s
+        # host loader) allocates pinned memory while the step is being captured; in the default global mode that call from
+        # ANOTHER thread invalidates the capture (cudaErrorStreamCaptureInvalidated, seen intermittently).
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
             if self.pipeline:
                 main = torch.cuda.current_stream()
                 self.geo_side.wait_stream(main)
