@@ -760,12 +760,22 @@ class PinnExecutor:
         if key not in self._seen:
             self._seen.add(key)
             return self.step(data, labels, domain, laplacian, geo=geo)
+        prev_stream = torch.cuda.current_stream()
         try:
             g = GraphedStep(self, data, labels, domain, laplacian, pipeline, geo=geo)
         except RuntimeError as exc:      # an op that cannot be captured: stay on the per-kernel launches for this signature
             import warnings
             warnings.warn(f'CUDA graph capture of the fused step failed ({exc}); launching eagerly')
-            torch.cuda.synchronize()
+            # a capture that dies half-way leaves torch's current stream on the (ended, invalidated) capture stream and the
+            # executor's side streams possibly inside it: go back to the caller's stream and to fresh side streams
+            torch.cuda.set_stream(prev_stream)
+            self.ctx.streams.clear()
+            self.ctx.side_stream = None
+            self.ctx.workspaces.clear()
+            try:
+                torch.cuda.synchronize()
+            except RuntimeError:
+                pass
             self._seen.discard(key)
             self._graphs[key] = _EagerStep(self, labels, laplacian)
             return self._graphs[key].run(data, domain, geo=geo)
