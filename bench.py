@@ -749,6 +749,10 @@ def main():
     # the auxiliary legs of the headline workload run BEFORE the other configs (N = 1 only, so every rank still enters
     # extra_configs together)
     ingest = None
+    legs_last = os.environ.get('PCFD_BENCH_LEGS_LAST', '0') == '1'      # diagnosis of the capture issue in DESIGN.md section 8
+    configs = None
+    if legs_last and not headline_only:
+        configs = extra_configs(env)
     if env.world == 1:
         try:
             ingest = ingest_leg(r['dev_batches'], r['labels'], shape['n_internal'], r['spec']['dims'], env.peaks)
@@ -762,7 +766,8 @@ def main():
             ingest = {'error': f'{type(e).__name__}: {e}'}
             torch.cuda.synchronize()
 
-    configs = None if headline_only else extra_configs(env)
+    if not legs_last:
+        configs = None if headline_only else extra_configs(env)
     if env.rank != 0:
         if env.world > 1:
             env.dist.destroy_process_group()

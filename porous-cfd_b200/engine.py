@@ -765,7 +765,9 @@ class PinnExecutor:
             g = GraphedStep(self, data, labels, domain, laplacian, pipeline, geo=geo)
         except RuntimeError as exc:      # an op that cannot be captured: stay on the per-kernel launches for this signature
             import warnings
-            warnings.warn(f'CUDA graph capture of the fused step failed ({exc}); launching eagerly')
+            first = exc.__context__ if exc.__context__ is not None else exc       # the error raised INSIDE the capture
+            warnings.warn(f'CUDA graph capture of the fused step failed ({type(first).__name__}: {str(first)[:400]}'
+                          + (f' -> {str(exc)[:200]}' if first is not exc else '') + '); launching eagerly')
             # a capture that dies half-way leaves torch's current stream on the (ended, invalidated) capture stream and the
             # executor's side streams possibly inside it: go back to the caller's stream and to fresh side streams
             torch.cuda.set_stream(prev_stream)
