@@ -28,6 +28,7 @@ reference's training_step computes as written).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -483,6 +484,8 @@ def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int,
                     geo_side = torch.cuda.Stream()
                     torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
+                gc.collect()          # no dead model (and its CUDA graph / memory pool) may be collected inside the capture
+                gc.disable()
                 with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                     if pipelined:
                         cap = torch.cuda.current_stream()
@@ -498,8 +501,10 @@ def run_workload(env: Env, config: str, shape: dict, b_per_gpu: int, steps: int,
                             for gk in cur_l:
                                 cur_l[gk].copy_(new_l[gk])
                 tail_in_graph = with_tail
+                gc.enable()
                 break
             except Exception as e:  # report and fall back (still the CUDA path)
+                gc.enable()
                 if rank == 0:
                     print(f'[bench] CUDA graph capture failed (tail in graph: {with_tail}; {type(e).__name__}: {e})', file=sys.stderr)
                 graph = None
@@ -702,6 +707,7 @@ def extra_configs(env: Env) -> list:
             torch.cuda.synchronize()
         out.append(entry)
         del r
+        gc.collect()                 # model <-> executor is a reference cycle: free its graphs and buffers now
         torch.cuda.empty_cache()
     return out
 

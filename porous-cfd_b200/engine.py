@@ -371,22 +371,34 @@ class GraphedStep:
             self.geo_side = torch.cuda.Stream(device=data.device)
         torch.cuda.current_stream().synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        # thread_local: only this thread's calls are checked against the capture.  A DataLoader's pin-memory thread (train()'s
-        # host loader) allocates pinned memory while the step is being captured; in the default global mode that call from
-        # ANOTHER thread invalidates the capture (cudaErrorStreamCaptureInvalidated, seen intermittently).
-        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
-            if self.pipeline:
-                main = torch.cuda.current_stream()
-                self.geo_side.wait_stream(main)
-                with torch.cuda.stream(self.geo_side):
-                    nxt = ex.geometry(None, labels, None, pos=self.pos_next)
-                self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
-                main.wait_stream(self.geo_side)
-                for cur, new in zip(self.geo, nxt):                          # after the step's last use of the old ones
-                    for k in cur:
-                        cur[k].copy_(new[k])
-            else:
-                self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
+        # Two precautions around the capture.  (1) Python's cyclic collector must not run inside it: a dead model of an
+        # earlier run (model <-> executor <-> GraphedStep is a reference cycle) owns a CUDAGraph and its memory pool, and
+        # collecting it DURING this capture frees device memory inside the capture -> cudaErrorStreamCaptureInvalidated
+        # (this torch no longer collects in torch.cuda.graph.__enter__; seen in bench.py after its configs block).  So:
+        # collect now, keep the collector off until the capture has ended.  (2) thread_local error mode: only this thread's
+        # calls are checked against the capture (a DataLoader's pin-memory thread may allocate meanwhile).
+        import gc
+        gc.collect()
+        gc_was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode='thread_local'):
+                if self.pipeline:
+                    main = torch.cuda.current_stream()
+                    self.geo_side.wait_stream(main)
+                    with torch.cuda.stream(self.geo_side):
+                        nxt = ex.geometry(None, labels, None, pos=self.pos_next)
+                    self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
+                    main.wait_stream(self.geo_side)
+                    for cur, new in zip(self.geo, nxt):                          # after the step's last use of the old ones
+                        for k in cur:
+                            cur[k].copy_(new[k])
+                else:
+                    self.result = ex.step(self.data, labels, self.domain, laplacian, geo=self.geo)
+
+        finally:
+            if gc_was_enabled:
+                gc.enable()
 
     def _announced(self, data: Tensor, domain: dict) -> bool:
         """Are these the tensors the previous call announced, unmodified since?  The announced tensors are kept
