@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -353,7 +354,7 @@ class GraphedStep:
 
     def __init__(self, ex: 'PinnExecutor', data: Tensor, labels: dict, domain: dict, laplacian: str, pipeline: bool = False,
                  geo: Optional[list] = None):
-        self.ex = ex
+        self.ex = weakref.proxy(ex)       # the executor owns this object (executor._graphs): no cycle
         self.data = torch.empty_like(data)
         self.domain = {k: torch.empty_like(v) for k, v in domain.items()}
         self.labels = labels
@@ -446,7 +447,7 @@ class _EagerStep:
     """Stand-in for GraphedStep when capture is not possible."""
 
     def __init__(self, ex, labels, laplacian):
-        self.ex, self.labels, self.laplacian = ex, labels, laplacian
+        self.ex, self.labels, self.laplacian = weakref.proxy(ex), labels, laplacian
 
     def run(self, data, domain, next_data=None, next_domain=None, geo=None):
         return self.ex.step(data, self.labels, domain, self.laplacian, geo=geo)
@@ -457,7 +458,10 @@ class PinnExecutor:
     `PorousPinnBase` once the model lives on a CUDA device."""
 
     def __init__(self, model):
-        self.model = model
+        # weak: model -> executor -> model would be a reference cycle, and a dropped model would then keep its CUDA graphs,
+        # memory pools and GBs of buffers alive until Python's cyclic collector happens to run (possibly inside a later
+        # graph capture, see GraphedStep); with a proxy the executor dies with its model
+        self.model = weakref.proxy(model)
         self.device = next(model.parameters()).device
         if self.device.type != 'cuda':
             raise _lib.PcfdError('the porous-cfd hot path only runs on a CUDA sm_100 device; move the model with '
