@@ -6,6 +6,8 @@ configured from these objects by `PorousPinnBase.residual_params`.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 from torch import Tensor, nn
 
@@ -117,7 +119,9 @@ class LossLogger:
 
     def __init__(self, module, *loss_labels: str):
         self.loss_labels = loss_labels
-        self.module = module
+        # weak: the model owns its loggers; a strong back-reference would make every model cyclic garbage that only
+        # Python's cyclic collector can free (with its CUDA graphs and buffers, see engine.GraphedStep)
+        self.module = weakref.proxy(module)
 
     def log(self, batch_size: int, *losses: Tensor):
         if len(losses) != len(self.loss_labels):

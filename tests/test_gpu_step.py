@@ -544,3 +544,34 @@ def test_one_launch_residual_equals_the_four_launch_form(name, mode):
     a, b = outs[True], outs[False]
     assert float((a[0] - b[0]).abs().max()) <= 2e-6 * float(b[0].abs().max())
     assert rel_l2(a[1].double().cpu(), b[1].double().cpu()) < 2e-6
+
+
+@pytest.mark.gpu
+def test_a_dropped_model_releases_its_executor_and_graphs_without_the_cyclic_collector():
+    """model -> executor -> model and executor -> GraphedStep -> executor are weak links: `del model` frees the executor,
+    its captured graphs and their buffers by reference counting (a cyclic model would be freed by Python's collector at an
+    arbitrary later time -- possibly inside another graph capture, which that invalidates)."""
+    import gc
+    import weakref
+    spec = synthetic.model_spec('tiny_pipn_pp')
+    _, _, params, _ = load_fixture('tiny_pipn_pp')
+    labels = synthetic.build_labels(spec['layout'])
+    data, _, domain = synthetic.make_batch(spec['layout'], seed=3, **TINY_SHAPE)
+    batch = FoamData(data, labels, domain).to('cuda')
+    was = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        model = cuda_model(spec, params).train()
+        model.cuda_graph = True
+        for step in range(3):
+            loss = model.training_step(batch, step)
+        loss.backward()
+        del loss
+        torch.cuda.synchronize()
+        refs = (weakref.ref(model), weakref.ref(model.executor), weakref.ref(next(iter(model.executor._graphs.values()))))
+        del model
+        assert all(r() is None for r in refs)
+    finally:
+        if was:
+            gc.enable()

@@ -42,3 +42,22 @@ def test_relobralo_restored_buffers_are_not_reinitialised():
     fresh = RelobraloScaler(5)
     fresh.load_state_dict(RelobraloScaler(5).state_dict())
     assert fresh._resume_step == 0                        # an untrained state keeps the first-step initialisation
+
+
+def test_models_are_freed_by_reference_counting():
+    """No reference cycle through the loss loggers: a dropped model is released at once, not when the cyclic collector
+    gets to it (on the GPU a cyclic model would keep its CUDA graphs and buffers alive until then)."""
+    import gc
+    import weakref
+    from porous_cfd_b200 import factory, synthetic
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        for name in ('tiny_pipn_pp', 'tiny_pigano', 'tiny_pipn', 'tiny_pigano_pp', 'tiny_manufactured_pp'):
+            model = factory.build_model(synthetic.model_spec(name))
+            ref = weakref.ref(model)
+            del model
+            assert ref() is None, name
+    finally:
+        if was:
+            gc.enable()
